@@ -1,0 +1,40 @@
+// core.cu -- error reporting and device checks shared by every entry point of libmarlb200.
+#include "common.cuh"
+#include <string.h>
+
+namespace marl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// No CPU fallback: a missing / non-Blackwell device is an error, never a silent slow path.
+int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("libmarlb200: no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return MARL_ECUDA;
+  }
+  if (device < 0 || device >= n) { set_error("libmarlb200: device %d out of range (0..%d)", device, n - 1); return MARL_EINVAL; }
+  cudaDeviceProp p;
+  MARL_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) {
+    set_error("libmarlb200: device %d is sm_%d%d; this build targets sm_100a (B200) only", device, p.major, p.minor);
+    return MARL_ECUDA;
+  }
+  MARL_CUDA_TRY(cudaSetDevice(device));
+  return MARL_OK;
+}
+
+}  // namespace marl
+
+extern "C" {
+int marl_version(void) { return MARL_ABI_VERSION; }
+const char* marl_last_error(void) { return marl::g_err; }
+}

@@ -1,0 +1,141 @@
+/*
+ * marl_b200.h -- C ABI of libmarlb200.so, the B200 (sm_100a) native hot path behind marlbase's plugin surface.
+ *
+ * The reference (marl-book/codebase, `marlbase`) is 100 % Python and has NO FFI boundary of its own: its
+ * plugin surface is Hydra `_target_` strings + Python duck typing.  This header is therefore
+ * the boundary a maintainer would bind (ctypes stub shown in INTEGRATION.md) to replace, one for one, the
+ * Python call sites cited on each entry point below.  Citations are path:line under /root/reference/.
+ *
+ * Conventions
+ *   - every pointer argument documented "device" is a CUDA device pointer owned by the caller (a torch tensor);
+ *     `stream` is a cudaStream_t passed as void*; calls enqueue work and return without synchronising;
+ *   - return value 0 = ok, negative = MARL_E*; the message is in marl_last_error() (thread local);
+ *   - handles are opaque, one host thread per GPU, not thread safe; no C++ / torch types cross the ABI;
+ *   - there is NO CPU fallback: every entry point fails with MARL_ECUDA if no sm_100-class device is present.
+ */
+#ifndef MARL_B200_H
+#define MARL_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARL_OK 0
+#define MARL_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define MARL_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define MARL_ENOMEM (-3)
+
+#define MARL_MAX_AGENTS 32
+#define MARL_ABI_VERSION 1
+
+int marl_version(void);
+const char* marl_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Level-Based Foraging, E environments per handle, one transition of all of them per launch.
+ * Replaces `env.reset()` / `env.step(actions)` of the gym.make()'d third-party `lbforaging` ForagingEnv under
+ * marlbase's wrapper stack:  marlbase/utils/envs.py:90-111 (single), :27-63 (AsyncVectorEnv), consumed at
+ * marlbase/dqn/train.py:203,217 and marlbase/ac/train.py:30,79-81; wrappers marlbase/utils/wrappers.py:13-45
+ * (RecordEpisodeStatistics), :106-108 (CooperativeReward); gymnasium TimeLimit at envs.py:95-96.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t rows, cols;          /* field_size */
+  int32_t n_agents;            /* players (<= MARL_MAX_AGENTS) */
+  int32_t max_num_food;
+  int32_t sight;               /* == rows: full observability; 2 for the "-2s" ids */
+  int32_t min_player_level, max_player_level;
+  int32_t min_food_level;
+  int32_t max_food_level;      /* <= 0: None -> sum of the (up to) 3 lowest player levels */
+  int32_t max_episode_steps;   /* env-internal horizon (50 for the registered ids) */
+  int32_t time_limit;          /* TimeLimit wrapper, env.time_limit in default.yaml:31; 0 = absent */
+  int32_t force_coop;
+  int32_t normalize_reward;
+  int32_t cooperative_reward;  /* CooperativeReward wrapper (configs/algorithm/vdn.yaml:6-8) */
+  double  penalty;
+} marl_lbf_cfg;
+
+typedef struct marl_lbf marl_lbf;
+
+/* Device-resident state, exposed for parity tests and checkpointing (all device pointers). */
+typedef struct {
+  int8_t*   field;        /* [E][field_pitch], row-major rows*cols cells then zero padding            */
+  int8_t*   players;      /* [E][N][4] = (row, col, level, 0)                                        */
+  int32_t*  step;         /* [E] current_step == TimeLimit's elapsed steps                           */
+  int32_t*  food_spawned; /* [E] sum of food levels at reset (reward normaliser)                      */
+  float*    ep_return;    /* [E][N] float32 running episode return (wrappers.py:33)                  */
+  int32_t*  ep_len;       /* [E]                                                                     */
+  uint32_t* episode_idx;  /* [E] resets performed so far                                             */
+  uint8_t*  active;       /* [E] 0 after the episode ended when autoreset is off                     */
+  int32_t   field_pitch;  /* bytes per env in `field` (rows*cols rounded up to 16)                    */
+  int32_t   n_envs;
+} marl_lbf_state;
+
+/* Trajectory store: the device layout of BOTH the episode replay ring (marlbase/dqn/train.py:19-124,
+ * capacity = buffer_size episodes) and the on-policy batch (marlbase/ac/train.py:36-52, capacity =
+ * parallel_envs).  Episode-major so that one sampled episode of one agent is one contiguous run. */
+typedef struct {
+  float*   obs;     /* [capacity][N][T+1][obs_dim] */
+  int32_t* act;     /* [capacity][N][T]            */
+  float*   rew;     /* [capacity][N][T]            */
+  uint8_t* done;    /* [capacity][T+1]             */
+  uint8_t* filled;  /* [capacity][T]               */
+  int32_t  capacity, n_agents, T, obs_dim;
+} marl_traj_view;
+
+int marl_lbf_create(const marl_lbf_cfg* cfg, int32_t n_envs, uint64_t seed, uint32_t env_gid0, int32_t device,
+                    marl_lbf** out);
+int marl_lbf_destroy(marl_lbf* env);
+int marl_lbf_obs_dim(const marl_lbf_cfg* cfg);             /* 3*max_num_food + 3*n_agents */
+int marl_lbf_state_ptrs(marl_lbf* env, marl_lbf_state* out);
+/* Overwrite the transition state (parity tests): host or device pointers are NOT mixed -- all device. */
+int marl_lbf_set_state(marl_lbf* env, const int8_t* field /*[E][rows*cols] dense*/, const int8_t* players,
+                       const int32_t* step, void* stream);
+
+/* Copy the state out into caller-owned DEVICE buffers (any may be NULL): field dense int8[E][rows*cols],
+ * players int8[E][N][4], step/food_spawned/ep_len int32[E], ep_return float[E][N], episode_idx uint32[E],
+ * active uint8[E]. */
+int marl_lbf_get_state(marl_lbf* env, int8_t* field, int8_t* players, int32_t* step, int32_t* food_spawned,
+                       float* ep_return, int32_t* ep_len, uint32_t* episode_idx, uint8_t* active, void* stream);
+
+/* env.reset(): reset_mask device uint8[E] or NULL (= all).  obs_out device float[E][N][obs_dim].
+ * If `traj` is non-NULL also performs ReplayBuffer.init_episode (dqn/train.py:65-71): obs slot 0 of
+ * ring slot (slot0 + e) % capacity. */
+int marl_lbf_reset(marl_lbf* env, const uint8_t* reset_mask, float* obs_out, const marl_traj_view* traj,
+                   int32_t slot0, void* stream);
+
+/* env.step(actions): actions device int32[E][N].  Outputs (device): obs_out float[E][N][obs_dim] (the new
+ * episode's first observation when autoreset fires, as gymnasium<1.0 vector envs do), rew_out float[E][N],
+ * done_out/trunc_out uint8[E], final_ret_out float[E][N] + final_len_out int32[E] written only for envs whose
+ * episode ended in this call (info["episode_returns"], info["episode_length"]). */
+int marl_lbf_step(marl_lbf* env, const int32_t* actions, float* obs_out, float* rew_out, uint8_t* done_out,
+                  uint8_t* trunc_out, float* final_ret_out, int32_t* final_len_out, int32_t autoreset,
+                  void* stream);
+
+/* Fused policy + transition + storage: one launch does, for every env,
+ *   model.act      dqn/model.py:94-116 (policy=1: epsilon-greedy over `values`) or
+ *                  ac/model.py:147-153 (policy=2: Categorical(logits=values).sample())
+ *   env.step       (as marl_lbf_step)
+ *   rb.add / batch_* writes   dqn/train.py:73-89, ac/train.py:90-99   (when traj != NULL)
+ * values: device float[E][N][n_actions] produced by marl_mlp_forward on the current obs buffer.
+ * actions_out (optional) receives the chosen actions. */
+typedef struct {
+  int32_t policy;                 /* 1 = eps-greedy on Q-values, 2 = categorical on logits */
+  float   epsilon;
+  int32_t n_actions;
+  int32_t use_proper_termination; /* dqn/train.py:219-225 */
+  int32_t autoreset;
+  int32_t clear_stale;            /* 0 = reference behaviour (a reused ring slot keeps stale tail) */
+  int32_t slot0;
+} marl_rollout_args;
+
+int marl_lbf_rollout_step(marl_lbf* env, const float* values, const marl_rollout_args* args,
+                          const marl_traj_view* traj, float* obs_inout, float* rew_out, uint8_t* done_out,
+                          uint8_t* trunc_out, float* final_ret_out, int32_t* final_len_out,
+                          int32_t* actions_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARL_B200_H */
