@@ -49,6 +49,30 @@ class RolloutArgs(C.Structure):
     ]
 
 
+class MlpCfg(C.Structure):
+    _fields_ = [("n_agents", C.c_int32), ("n_nets", C.c_int32), ("agent_net", C.c_int32 * 32), ("in_dim", C.c_int32),
+                ("hidden", C.c_int32), ("out_dim", C.c_int32)]
+
+
+class DqnHP(C.Structure):
+    _fields_ = [("lr", C.c_float), ("gamma", C.c_float), ("grad_clip", C.c_float), ("double_q", C.c_int32),
+                ("target_update_interval_or_tau", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("mixer", C.c_int32)]
+
+
+class _DevArray:
+    """Zero-copy torch view of library-owned device memory through the CUDA array interface."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def device_view(ptr: int, n: int, device, typestr: str = "<f4"):
+    import torch
+
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+
+
 def lib():
     """Load libmarlb200.so; raise loudly when it is absent (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
     global _lib

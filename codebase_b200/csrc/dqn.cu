@@ -1,0 +1,296 @@
+// dqn.cu -- C ABI of the IDQN / VDN learner (marl_dqn_*), host-side orchestration of the fused kernels.
+//
+// Replaces marlbase/dqn/model.py: QNetwork (14-196) and VDNetwork (199-269) -- act's forward pass, _compute_loss,
+// update (zero_grad/backward/clip/Adam), update_target/hard_update/soft_update -- and ReplayBuffer.sample's index
+// draw + gather (marlbase/dqn/train.py:94-124).
+#include "learner.cuh"
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+namespace marl {
+
+// ---- replay sampling: np.random.randint(0, len(rb), batch) with replacement (dqn/train.py:95) ------------------
+__global__ void replay_sample_kernel(uint64_t seed, uint64_t update_idx, int batch, int n_valid, int32_t* idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const u32x4 b = philox4x32_10((uint32_t)update_idx, (uint32_t)(update_idx >> 32), (uint32_t)(i >> 2), 0u, (uint32_t)seed, (uint32_t)(seed >> 32) ^ kTagSample);
+  idx[i] = (int32_t)bounded(pick(b, i & 3), (uint32_t)n_valid);
+}
+
+// ---- VDN: agent-coupled TD error (marlbase/dqn/model.py:224-269) ------------------------------------------------
+struct VdnTdParams {
+  const float* q; const float* tq;  // [N][B][T+1][A]
+  TrajView traj; const int32_t* idx; int B, N, A; float gamma; int double_q;
+  float* td;         // [B][T] = 2 * delta * filled
+  float* loss_part;  // [gridDim][2]
+};
+
+__global__ void __launch_bounds__(256) vdn_td_kernel(VdnTdParams p) {
+  __shared__ float red[512];
+  const int T = p.traj.T, i = blockIdx.x * 256 + threadIdx.x;
+  float loss = 0.f, fill = 0.f;
+  if (i < p.B * T) {
+    const int b = i / T, t = i - b * T;
+    const size_t ep = (size_t)p.idx[b];
+    float chosen = 0.f, tsum = 0.f;
+    for (int a = 0; a < p.N; ++a) {
+      const size_t row = ((size_t)a * p.B + b) * (T + 1) + t;
+      const float* q0 = p.q + row * p.A; const float* q1 = q0 + p.A; const float* t1 = p.tq + (row + 1) * p.A;
+      chosen += q0[p.traj.act[(ep * p.N + a) * T + t]];
+      if (p.double_q) {
+        int best = 0; float bv = q1[0];
+        for (int o = 1; o < p.A; ++o) if (q1[o] > bv) { bv = q1[o]; best = o; }
+        tsum += t1[best];
+      } else {
+        float m = t1[0];
+        for (int o = 1; o < p.A; ++o) m = fmaxf(m, t1[o]);
+        tsum += m;
+      }
+    }
+    const float filled = (float)p.traj.filled[ep * T + t];
+    const float y = p.traj.rew[(ep * p.N + 0) * T + t] + p.gamma * tsum * (1.f - (float)p.traj.done[ep * (T + 1) + t + 1]);
+    const float delta = chosen - y;
+    loss = delta * delta * filled; fill = filled;
+    p.td[i] = 2.f * delta * filled;
+  }
+  red[threadIdx.x] = loss; red[256 + threadIdx.x] = fill;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { red[threadIdx.x] += red[threadIdx.x + s]; red[256 + threadIdx.x] += red[256 + threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { p.loss_part[2 * blockIdx.x] = red[0]; p.loss_part[2 * blockIdx.x + 1] = red[256]; }
+}
+
+// ---- host-side planning -----------------------------------------------------------------------------------------
+struct NetSet {
+  int n_agents = 0, n_nets = 0, in = 0, out = 0;
+  int agent_net[MARL_MAX_AGENTS];
+  NetLayout lay;
+};
+
+// Split `n_cta_max` CTAs over the networks in proportion to their row counts; every CTA gets >= min_units units.
+static RowPlan make_plan(const NetSet& ns, int units_per_agent, int unit_rows, int n_cta_max, int min_units) {
+  RowPlan p; memset(&p, 0, sizeof(p));
+  p.n_nets = ns.n_nets; p.unit_rows = unit_rows; p.units_per_agent = units_per_agent;
+  int s = 0;
+  for (int k = 0; k < ns.n_nets; ++k) {
+    p.slot_begin[k] = s;
+    for (int a = 0; a < ns.n_agents; ++a) if (ns.agent_net[a] == k) p.slot_agent[s++] = a;
+  }
+  p.slot_begin[ns.n_nets] = s;
+  long long total = (long long)ns.n_agents * units_per_agent;
+  int c = 0;
+  for (int k = 0; k < ns.n_nets; ++k) {
+    const long long units = (long long)(p.slot_begin[k + 1] - p.slot_begin[k]) * units_per_agent;
+    long long want = (long long)n_cta_max * units / (total > 0 ? total : 1);
+    const long long cap = (units + min_units - 1) / min_units;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    p.cta_begin[k] = c;
+    c += (int)want;
+  }
+  p.cta_begin[ns.n_nets] = c;
+  return p;
+}
+
+static TrajView to_view(const marl_traj_view* t) {
+  TrajView v; v.obs = t->obs; v.act = t->act; v.rew = t->rew; v.done = t->done; v.filled = t->filled;
+  v.capacity = t->capacity; v.N = t->n_agents; v.T = t->T; v.D = t->obs_dim;
+  return v;
+}
+
+}  // namespace marl
+
+using namespace marl;
+
+struct marl_dqn {
+  NetSet ns;
+  marl_dqn_hp hp;
+  int device = 0, n_sm = 148, max_batch = 0, max_T = 0;
+  int64_t n_params = 0;  // n_nets * P
+  int scratch_pitch = 0;
+  float *theta = nullptr, *theta_tgt = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
+  float *scratch = nullptr, *loss_part = nullptr, *tq = nullptr, *q_all = nullptr, *td = nullptr, *loss_dev = nullptr;
+  int32_t* idx = nullptr;
+  int64_t updates = 0, last_target_update = 0;
+  RowPlan train_plan; int n_loss_parts = 0;
+};
+
+static int dqn_alloc(float** p, size_t n_floats) {
+  cudaError_t e = cudaMalloc((void**)p, n_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, n_floats * sizeof(float));
+  if (e != cudaSuccess) { set_error("marl_dqn: cudaMalloc(%zu floats) failed: %s", n_floats, cudaGetErrorString(e)); return MARL_ENOMEM; }
+  return MARL_OK;
+}
+
+static int launch_forward(const NetSet& ns, int n_sm, const RowPlan& plan, const RowSource& src, const float* theta, float* out, cudaStream_t st) {
+  FwdParams fp; fp.plan = plan; fp.src = src; fp.theta = theta; fp.lay = ns.lay; fp.out = out;
+  (void)n_sm;
+  return launch_mlp_forward(fp, st);
+}
+
+extern "C" {
+
+int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_batch, int32_t max_T, int32_t device, marl_dqn** out) {
+  MARL_REQUIRE(cfg && hp && out, "marl_dqn_create: NULL argument");
+  *out = nullptr;
+  MARL_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= MARL_MAX_AGENTS, "marl_dqn_create: n_agents out of range");
+  MARL_REQUIRE(cfg->n_nets >= 1 && cfg->n_nets <= cfg->n_agents, "marl_dqn_create: n_nets out of range");
+  MARL_REQUIRE(cfg->hidden == kHidden, "marl_dqn_create: only layers=[128,128] is implemented on the B200 path (got hidden=%d)", cfg->hidden);
+  MARL_REQUIRE(cfg->in_dim >= 1 && cfg->in_dim <= 16, "marl_dqn_create: obs dim %d not supported yet (1..16)", cfg->in_dim);
+  MARL_REQUIRE(cfg->out_dim >= 1 && cfg->out_dim <= kOutPad, "marl_dqn_create: n_actions %d not supported (1..%d)", cfg->out_dim, kOutPad);
+  MARL_REQUIRE(max_batch >= 1 && max_T >= 1, "marl_dqn_create: max_batch/max_T must be >= 1");
+  MARL_REQUIRE(hp->mixer == 0 || hp->mixer == 1, "marl_dqn_create: mixer must be 0 (independent) or 1 (VDN)");
+  for (int a = 0; a < cfg->n_agents; ++a) MARL_REQUIRE(cfg->agent_net[a] >= 0 && cfg->agent_net[a] < cfg->n_nets, "marl_dqn_create: agent_net[%d] out of range", a);
+  if (int rc = check_device(device)) return rc;
+  marl_dqn* h = new marl_dqn();
+  h->ns.n_agents = cfg->n_agents; h->ns.n_nets = cfg->n_nets; h->ns.in = cfg->in_dim; h->ns.out = cfg->out_dim;
+  memcpy(h->ns.agent_net, cfg->agent_net, sizeof(int) * MARL_MAX_AGENTS);
+  h->ns.lay = NetLayout::make(cfg->in_dim, cfg->out_dim);
+  h->hp = *hp; h->device = device; h->max_batch = max_batch; h->max_T = max_T;
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); h->n_sm = prop.multiProcessorCount;
+  h->n_params = (int64_t)cfg->n_nets * h->ns.lay.P;
+  h->scratch_pitch = (h->ns.lay.P + 3) & ~3;
+  const size_t rows = (size_t)cfg->n_agents * max_batch * (max_T + 1);
+  int rc = 0;
+  rc |= dqn_alloc(&h->theta, h->n_params); rc |= dqn_alloc(&h->theta_tgt, h->n_params);
+  rc |= dqn_alloc(&h->m, h->n_params); rc |= dqn_alloc(&h->v, h->n_params); rc |= dqn_alloc(&h->grad, h->n_params + 2);
+  rc |= dqn_alloc(&h->scratch, (size_t)h->n_sm * h->scratch_pitch);
+  rc |= dqn_alloc(&h->loss_part, 2 * ((size_t)h->n_sm + (size_t)max_batch * max_T / 256 + 2));
+  rc |= dqn_alloc(&h->tq, rows * cfg->out_dim);
+  rc |= dqn_alloc(&h->loss_dev, 2);
+  if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
+  rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
+  if (rc) { marl_dqn_destroy(h); return MARL_ENOMEM; }
+  if (int rc2 = learner_kernels_init(cfg->in_dim)) { marl_dqn_destroy(h); return rc2; }
+  *out = h;
+  return MARL_OK;
+}
+
+int marl_dqn_destroy(marl_dqn* h) {
+  if (!h) return MARL_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->idx);
+  delete h;
+  return MARL_OK;
+}
+
+int marl_dqn_param_ptrs(marl_dqn* h, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_param_ptrs: NULL handle");
+  if (theta) *theta = h->theta; if (theta_tgt) *theta_tgt = h->theta_tgt; if (adam_m) *adam_m = h->m; if (adam_v) *adam_v = h->v;
+  if (grad) *grad = h->grad; if (n_params) *n_params = h->n_params;
+  return MARL_OK;
+}
+
+int marl_dqn_sync_target(marl_dqn* h, void* stream) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_sync_target: NULL handle");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  MARL_CUDA_TRY(cudaMemcpyAsync(h->theta_tgt, h->theta, h->n_params * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MARL_OK;
+}
+
+int marl_dqn_forward(marl_dqn* h, const float* obs, int32_t n_envs, int32_t use_target, float* q_out, void* stream) {
+  MARL_REQUIRE(h && obs && q_out && n_envs >= 1, "marl_dqn_forward: bad argument");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  const RowPlan plan = make_plan(h->ns, n_envs, 1, h->n_sm, 32);
+  RowSource src; memset(&src, 0, sizeof(src));
+  src.mode = 0; src.dense = obs; src.E = n_envs; src.N = h->ns.n_agents; src.D = h->ns.in;
+  return launch_forward(h->ns, h->n_sm, plan, src, use_target ? h->theta_tgt : h->theta, q_out, (cudaStream_t)stream);
+}
+
+int marl_replay_sample(uint64_t seed, uint64_t update_idx, int32_t batch, int32_t n_valid, int32_t* idx_out, void* stream) {
+  MARL_REQUIRE(idx_out && batch >= 1 && n_valid >= 1, "marl_replay_sample: bad argument");
+  replay_sample_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, update_idx, batch, n_valid, idx_out);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, void* stream) {
+  MARL_REQUIRE(h && traj && episode_idx, "marl_dqn_update_grads: NULL argument");
+  MARL_REQUIRE(batch >= 1 && batch <= h->max_batch, "marl_dqn_update_grads: batch %d exceeds max_batch %d", batch, h->max_batch);
+  MARL_REQUIRE(traj->T >= 1 && traj->T <= h->max_T, "marl_dqn_update_grads: T %d exceeds max_T %d", traj->T, h->max_T);
+  MARL_REQUIRE(traj->n_agents == h->ns.n_agents && traj->obs_dim == h->ns.in, "marl_dqn_update_grads: trajectory shape mismatch");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = traj->T;
+  const int min_units = (64 + T) / (T + 1) > 0 ? (64 + T) / (T + 1) : 1;
+  const RowPlan plan = make_plan(h->ns, batch, T + 1, h->n_sm, min_units);
+  RowSource src; memset(&src, 0, sizeof(src));
+  src.mode = 1; src.traj = to_view(traj); src.idx = episode_idx; src.N = h->ns.n_agents; src.D = h->ns.in;
+  // target network on every gathered row (dqn/model.py:132-134)
+  if (int rc = launch_forward(h->ns, h->n_sm, plan, src, h->theta_tgt, h->tq, st)) return rc;
+  int n_loss_parts = plan.cta_begin[plan.n_nets];
+  const float* td_ext = nullptr;
+  float* loss_part = h->loss_part;
+  if (h->hp.mixer == 1) {  // VDN: online Q-values of all agents first, then the agent-summed TD error
+    if (int rc = launch_forward(h->ns, h->n_sm, plan, src, h->theta, h->q_all, st)) return rc;
+    VdnTdParams vp; vp.q = h->q_all; vp.tq = h->tq; vp.traj = src.traj; vp.idx = episode_idx; vp.B = batch; vp.N = h->ns.n_agents; vp.A = h->ns.out;
+    vp.gamma = h->hp.gamma; vp.double_q = h->hp.double_q; vp.td = h->td;
+    const int vb = (batch * T + 255) / 256;
+    vp.loss_part = h->loss_part + 2 * (size_t)n_loss_parts;  // the train kernel's parts read as zero in this mode
+    vdn_td_kernel<<<vb, 256, 0, st>>>(vp);
+    MARL_CUDA_TRY(cudaGetLastError());
+    n_loss_parts += vb;
+    td_ext = h->td;
+  }
+  DqnTrainParams tp; tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext;
+  tp.gamma = h->hp.gamma; tp.double_q = h->hp.double_q; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch; tp.loss_part = loss_part;
+  if (int rc = launch_dqn_train(tp, st)) return rc;
+  ReduceParams rp; rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->ns.n_nets; rp.P = h->ns.lay.P; rp.scratch_pitch = h->scratch_pitch;
+  memcpy(rp.cta_begin, plan.cta_begin, sizeof(rp.cta_begin));
+  rp.n_loss_parts = n_loss_parts; rp.grad = h->grad;
+  return launch_grad_reduce(rp, st);
+}
+
+int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_update_apply: NULL handle");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  h->updates += 1;
+  AdamParams ap; ap.theta = h->theta; ap.theta_tgt = h->theta_tgt; ap.m = h->m; ap.v = h->v; ap.grad = h->grad; ap.n = (int)h->n_params;
+  ap.lr = h->hp.lr; ap.beta1 = h->hp.beta1; ap.beta2 = h->hp.beta2; ap.eps = h->hp.eps; ap.grad_clip = h->hp.grad_clip;
+  ap.bc1 = (float)(1.0 - pow((double)h->hp.beta1, (double)h->updates));
+  ap.bc2_sqrt = (float)sqrt(1.0 - pow((double)h->hp.beta2, (double)h->updates));
+  // update_target (dqn/model.py:176-185)
+  const float tu = h->hp.target_update_interval_or_tau;
+  ap.target_mode = 0; ap.tau = tu;
+  if (tu > 1.0f && (float)(h->updates - h->last_target_update) >= tu) { ap.target_mode = 1; h->last_target_update = h->updates; }
+  else if (tu < 1.0f) ap.target_mode = 2;
+  ap.loss_out = loss_out ? loss_out : h->loss_dev;
+  return launch_adam(ap, (cudaStream_t)stream);
+}
+
+int marl_dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, float* loss_out, void* stream) {
+  if (int rc = marl_dqn_update_grads(h, traj, episode_idx, batch, stream)) return rc;
+  return marl_dqn_update_apply(h, loss_out, stream);
+}
+
+/* n_updates back-to-back updates with on-device replay sampling: the `rb.sample(); model.update()` pair of
+ * marlbase/dqn/train.py:308-311 repeated, without returning to Python in between. */
+int marl_dqn_update_n(marl_dqn* h, const marl_traj_view* traj, int32_t batch, int32_t n_valid, uint64_t seed, uint64_t first_update_idx,
+                      int32_t n_updates, float* loss_out, void* stream) {
+  MARL_REQUIRE(h && traj && n_updates >= 0, "marl_dqn_update_n: bad argument");
+  MARL_REQUIRE(n_valid >= 1 && n_valid <= traj->capacity, "marl_dqn_update_n: n_valid %d out of range", n_valid);
+  for (int u = 0; u < n_updates; ++u) {
+    if (int rc = marl_replay_sample(seed, first_update_idx + (uint64_t)u, batch, n_valid, h->idx, stream)) return rc;
+    if (int rc = marl_dqn_update(h, traj, h->idx, batch, loss_out, stream)) return rc;
+  }
+  return MARL_OK;
+}
+
+int marl_dqn_counters(marl_dqn* h, int64_t* updates, int64_t* last_target_update) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_counters: NULL handle");
+  if (updates) *updates = h->updates;
+  if (last_target_update) *last_target_update = h->last_target_update;
+  return MARL_OK;
+}
+
+int marl_dqn_set_counters(marl_dqn* h, int64_t updates, int64_t last_target_update) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_set_counters: NULL handle");
+  h->updates = updates; h->last_target_update = last_target_update;
+  return MARL_OK;
+}
+
+}  // extern "C"

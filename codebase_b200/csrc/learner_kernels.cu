@@ -1,0 +1,371 @@
+// learner_kernels.cu -- the fused learner kernels (sm_100a).
+//
+//  mlp_forward_kernel   per-agent MLP inference on gathered rows: model.act's critic/actor forward
+//                       (marlbase/dqn/model.py:99, marlbase/ac/model.py:148-149) and the target-network pass of the
+//                       learner (marlbase/dqn/model.py:132-134, marlbase/ac/model.py:190-193).  Replay gather
+//                       (marlbase/dqn/train.py:94-124) is fused into the tile load.
+//  dqn_train_kernel     QNetwork._compute_loss + loss.backward() (marlbase/dqn/model.py:118-168): gather, online
+//                       forward, double-Q TD target, MSE, masked mean numerator, full backward; every CTA keeps its
+//                       network's weights resident in shared memory and walks its episodes tile by tile.
+//  grad_reduce_kernel   deterministic sum of the per-CTA gradient partials (+ loss / filled sums).
+//  adam_kernel          clip_grad_norm_ + Adam.step + update_target (marlbase/dqn/model.py:169-196).
+//
+// Persistent CTAs, one per SM (148 on B200) split across networks; FP32 FFMA register-tiled GEMMs (see mlp.cuh).
+#include "learner.cuh"
+
+namespace marl {
+
+// ------------------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(FwdParams p) {
+  extern __shared__ __align__(16) float smem[];
+  WeightSmem<KP> w(smem);
+  float* X = smem + WeightSmem<KP>::kFloats;
+  float* H1 = X + kTileRows * KP;
+  float* H2 = H1 + kTileRows * kHidden;
+  float* Q = H2 + kTileRows * kHidden;
+  const ThreadCoord tc;
+  int net, row_begin, row_end;
+  cta_rows(p.plan, net, row_begin, row_end);
+  if (row_begin >= row_end) return;
+  w.load(p.theta + (size_t)net * p.lay.P, p.lay);
+  for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
+    const int nrows = min(kTileRows, row_end - vr0);
+    __syncthreads();
+    gather_tile<KP>(X, p.plan, p.src, net, vr0, nrows);
+    __syncthreads();
+    mlp_forward_tile<KP>(X, H1, H2, Q, w, tc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrows * p.lay.out; i += kMlpThreads) {
+      const int r = i / p.lay.out, o = i - r * p.lay.out;
+      int agent, unit, off;
+      decode_row(p.plan, net, vr0 + r, agent, unit, off);
+      const size_t dst = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent)
+                                         : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
+      p.out[dst * p.lay.out + o] = Q[r * kOutPad + o];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-CTA gradient partial: first tile stores, later tiles accumulate (plain loads/stores: the region is private)
+__device__ __forceinline__ void rmw(float* dst, float v, bool first) { *dst = first ? v : (*dst + v); }
+__device__ __forceinline__ void rmw4(float* dst, float4 v, bool first) {
+  float4* d = reinterpret_cast<float4*>(dst);
+  if (!first) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+  *d = v;
+}
+
+// Backward of one tile.  On entry: X, H1, H2 hold the forward activations, DQ[128][8] holds dLoss/dq (zero rows
+// beyond the valid ones).  gs = this CTA's gradient partial [P].  Uses DQ as scratch after it is consumed.
+template <int KP>
+__device__ __forceinline__ void mlp_backward_tile(const float* X, float* H1, float* H2, float* DQ, const WeightSmem<KP>& w, const NetLayout& lay,
+                                                  float* gs, bool first, const ThreadCoord& tc) {
+  const int t = threadIdx.x;
+  // ---- dW3[o][j] = sum_r dq[r][o] * h2[r][j];  db3[o] = sum_r dq[r][o] --------------------------------------
+  {
+    const int j = t & (kHidden - 1), o0 = (t >> 7) * 4;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < kTileRows; ++r) {
+      const float h = at1<kHidden>(H2, r, j);
+      const float4 d = *reinterpret_cast<const float4*>(DQ + r * kOutPad + o0);
+      g0 = fmaf(d.x, h, g0); g1 = fmaf(d.y, h, g1); g2 = fmaf(d.z, h, g2); g3 = fmaf(d.w, h, g3);
+    }
+    if (o0 + 0 < lay.out) rmw(gs + lay.w3 + (o0 + 0) * kHidden + j, g0, first);
+    if (o0 + 1 < lay.out) rmw(gs + lay.w3 + (o0 + 1) * kHidden + j, g1, first);
+    if (o0 + 2 < lay.out) rmw(gs + lay.w3 + (o0 + 2) * kHidden + j, g2, first);
+    if (o0 + 3 < lay.out) rmw(gs + lay.w3 + (o0 + 3) * kHidden + j, g3, first);
+    if (t < lay.out) {
+      float s = 0.f;
+      for (int r = 0; r < kTileRows; ++r) s += DQ[r * kOutPad + t];
+      rmw(gs + lay.b3 + t, s, first);
+    }
+  }
+  __syncthreads();
+  // ---- dh2[r][j] = (sum_o dq[r][o] * W3[o][j]) * (h2[r][j] > 0), in place over H2; db2 partials ----------------
+  float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int c = t & 31, rbase = t >> 5;
+    float4 wv[kOutPad];
+#pragma unroll
+    for (int o = 0; o < kOutPad; ++o) wv[o] = reinterpret_cast<const float4*>(w.w3 + o * kHidden)[c];
+#pragma unroll 2
+    for (int it = 0; it < kTileRows / 8; ++it) {
+      const int r = rbase + 8 * it;
+      const float4 d0 = *reinterpret_cast<const float4*>(DQ + r * kOutPad), d1 = *reinterpret_cast<const float4*>(DQ + r * kOutPad + 4);
+      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < kOutPad; ++o) {
+        g.x = fmaf(dv[o], wv[o].x, g.x); g.y = fmaf(dv[o], wv[o].y, g.y); g.z = fmaf(dv[o], wv[o].z, g.z); g.w = fmaf(dv[o], wv[o].w, g.w);
+      }
+      float4& h = at4<kHidden>(H2, r, c);
+      g.x = h.x > 0.f ? g.x : 0.f; g.y = h.y > 0.f ? g.y : 0.f; g.z = h.z > 0.f ? g.z : 0.f; g.w = h.w > 0.f ? g.w : 0.f;
+      h = g;
+      colsum.x += g.x; colsum.y += g.y; colsum.z += g.z; colsum.w += g.w;
+    }
+  }
+  __syncthreads();  // dq fully consumed -> reuse DQ as the [8][128] reduction buffer
+  *reinterpret_cast<float4*>(DQ + (t >> 5) * kHidden + (t & 31) * 4) = colsum;
+  __syncthreads();
+  if (t < kHidden) {
+    float s = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) s += DQ[wq * kHidden + t];
+    rmw(gs + lay.b2 + t, s, first);
+  }
+  // ---- dW2[m][n] = sum_r dh2[r][m] * h1[r][n] ------------------------------------------------------------------
+  {
+    float acc[8][8];
+    zero_acc(acc);
+    gemm_tn<kHidden, kHidden>(H2, H1, kTileRows, tc, acc);
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      float* row = gs + lay.w2 + tn_row(tc, mi) * kHidden;
+      rmw4(row + tn_col(tc, 0), make_float4(acc[mi][0], acc[mi][1], acc[mi][2], acc[mi][3]), first);
+      rmw4(row + tn_col(tc, 4), make_float4(acc[mi][4], acc[mi][5], acc[mi][6], acc[mi][7]), first);
+    }
+  }
+  __syncthreads();  // H1 no longer needed as a GEMM operand; DQ reduction buffer consumed
+  // ---- dh1[r][n] = (sum_k dh2[r][k] * W2[k][n]) * (h1[r][n] > 0), in place over H1; db1 ----------------------------
+  {
+    float acc[8][8];
+    zero_acc(acc);
+    gemm_nn(H2, w.w2, tc, acc);
+    const int r0 = tc.wy * 32 + tc.ty, nc = tc.wx * 16 + tc.tx;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4& h0 = at4<kHidden>(H1, r0 + 4 * i, nc);
+      float4& h1 = at4<kHidden>(H1, r0 + 4 * i, nc + 8);
+      float4 g0, g1;
+      g0.x = h0.x > 0.f ? acc[i][0] : 0.f; g0.y = h0.y > 0.f ? acc[i][1] : 0.f; g0.z = h0.z > 0.f ? acc[i][2] : 0.f; g0.w = h0.w > 0.f ? acc[i][3] : 0.f;
+      g1.x = h1.x > 0.f ? acc[i][4] : 0.f; g1.y = h1.y > 0.f ? acc[i][5] : 0.f; g1.z = h1.z > 0.f ? acc[i][6] : 0.f; g1.w = h1.w > 0.f ? acc[i][7] : 0.f;
+      h0 = g0; h1 = g1;
+      cs[0] += g0.x; cs[1] += g0.y; cs[2] += g0.z; cs[3] += g0.w; cs[4] += g1.x; cs[5] += g1.y; cs[6] += g1.z; cs[7] += g1.w;
+    }
+    // sum over the four ty lanes (lane bits 3,4), then one partial per row-warp into DQ[wy][n]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cs[j] += __shfl_xor_sync(0xFFFFFFFFu, cs[j], 8);
+      cs[j] += __shfl_xor_sync(0xFFFFFFFFu, cs[j], 16);
+    }
+    if (tc.ty == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) DQ[tc.wy * kHidden + tn_col(tc, j)] = cs[j];
+    }
+  }
+  __syncthreads();
+  if (t < kHidden) rmw(gs + lay.b1 + t, DQ[t] + DQ[kHidden + t] + DQ[2 * kHidden + t] + DQ[3 * kHidden + t], first);
+  // ---- dW1[m][i] = sum_r dh1[r][m] * x[r][i] ---------------------------------------------------------------------
+  {
+    const int mg = t >> 4, i0 = t & 15;
+    float acc[KP / 16][8];
+#pragma unroll
+    for (int ii = 0; ii < KP / 16; ++ii)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[ii][q] = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < kTileRows; ++r) {
+      const float4 a0 = at4<kHidden>(H1, r, 2 * mg), a1 = at4<kHidden>(H1, r, 2 * mg + 1);
+#pragma unroll
+      for (int ii = 0; ii < KP / 16; ++ii) {
+        const float x = at1<KP>(X, r, i0 + 16 * ii);
+        acc[ii][0] = fmaf(a0.x, x, acc[ii][0]); acc[ii][1] = fmaf(a0.y, x, acc[ii][1]); acc[ii][2] = fmaf(a0.z, x, acc[ii][2]); acc[ii][3] = fmaf(a0.w, x, acc[ii][3]);
+        acc[ii][4] = fmaf(a1.x, x, acc[ii][4]); acc[ii][5] = fmaf(a1.y, x, acc[ii][5]); acc[ii][6] = fmaf(a1.z, x, acc[ii][6]); acc[ii][7] = fmaf(a1.w, x, acc[ii][7]);
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < KP / 16; ++ii) {
+      const int i = i0 + 16 * ii;
+      if (i < lay.in) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rmw(gs + lay.w1 + (mg * 8 + q) * lay.in + i, acc[ii][q], first);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(kMlpThreads, 1) dqn_train_kernel(DqnTrainParams p) {
+  extern __shared__ __align__(16) float smem[];
+  WeightSmem<KP> w(smem);
+  float* X = smem + WeightSmem<KP>::kFloats;
+  float* H1 = X + kTileRows * KP;
+  float* H2 = H1 + kTileRows * kHidden;
+  float* Q = H2 + kTileRows * kHidden;  // q-values, then dq, then reduction scratch
+  float* carry = Q + kTileRows * kOutPad;  // q-values of the first row of the previously processed (higher) tile
+  const ThreadCoord tc;
+  const int t = threadIdx.x;
+  int net, row_begin, row_end;
+  cta_rows(p.plan, net, row_begin, row_end);
+  float* gs = p.scratch + (size_t)blockIdx.x * p.scratch_pitch;
+  float loss_acc = 0.f, filled_acc = 0.f;
+  if (row_begin >= row_end) {  // idle CTA: its partial must still read as zero
+    for (int i = t; i < p.lay.P; i += kMlpThreads) gs[i] = 0.f;
+    if (t == 0) { p.loss_part[2 * blockIdx.x] = 0.f; p.loss_part[2 * blockIdx.x + 1] = 0.f; }
+    return;
+  }
+  w.load(p.theta + (size_t)net * p.lay.P, p.lay);
+  const int T = p.src.traj.T, A = p.lay.out, B = p.plan.units_per_agent;
+  bool first = true;
+  // tiles from the top of the chunk downwards, so that q(t+1) of a tile's last row is already known
+  for (int vr_hi = row_end; vr_hi > row_begin; vr_hi -= kTileRows) {
+    const int vr0 = max(row_begin, vr_hi - kTileRows), nrows = vr_hi - vr0;
+    __syncthreads();
+    gather_tile<KP>(X, p.plan, p.src, net, vr0, nrows);
+    __syncthreads();
+    mlp_forward_tile<KP>(X, H1, H2, Q, w, tc);
+    __syncthreads();
+    // ---- TD head: one thread per row -------------------------------------------------------------------------
+    float dq[kOutPad];
+#pragma unroll
+    for (int o = 0; o < kOutPad; ++o) dq[o] = 0.f;
+    float q_first[kOutPad];
+    if (t == 0) {
+#pragma unroll
+      for (int o = 0; o < kOutPad; ++o) q_first[o] = Q[o];
+    }
+    if (t < nrows) {
+      int agent, b, tt;
+      decode_row(p.plan, net, vr0 + t, agent, b, tt);
+      if (tt < T) {
+        const size_t ep = (size_t)p.src.idx[b];
+        const TrajView& tv = p.src.traj;
+        const int act = tv.act[(ep * tv.N + agent) * T + tt];
+        const float filled = (float)tv.filled[ep * T + tt];
+        float g;
+        if (p.td_ext) {  // VDN: the agent-coupled TD error was computed by vdn_td_kernel
+          g = p.td_ext[(size_t)b * T + tt];
+        } else {
+          const float rew = tv.rew[(ep * tv.N + agent) * T + tt];
+          const float done1 = (float)tv.done[ep * (T + 1) + tt + 1];
+          const float* qn = (t + 1 < nrows) ? (Q + (t + 1) * kOutPad) : carry;
+          const float* tq = p.tq + (((size_t)agent * B + b) * (T + 1) + tt + 1) * A;
+          float tsel;
+          if (p.double_q) {
+            int best = 0; float bv = qn[0];
+            for (int o = 1; o < A; ++o) if (qn[o] > bv) { bv = qn[o]; best = o; }
+            tsel = tq[best];
+          } else {
+            tsel = tq[0];
+            for (int o = 1; o < A; ++o) tsel = fmaxf(tsel, tq[o]);
+          }
+          const float y = rew + p.gamma * tsel * (1.f - done1);
+          const float delta = Q[t * kOutPad + act] - y;
+          loss_acc += delta * delta * filled;
+          if (agent == 0) filled_acc += filled;
+          g = 2.f * delta * filled;
+        }
+#pragma unroll
+        for (int o = 0; o < kOutPad; ++o) dq[o] = (o == act) ? g : 0.f;
+      }
+    }
+    __syncthreads();
+    if (t < kTileRows) {
+      *reinterpret_cast<float4*>(Q + t * kOutPad) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+      *reinterpret_cast<float4*>(Q + t * kOutPad + 4) = make_float4(dq[4], dq[5], dq[6], dq[7]);
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int o = 0; o < kOutPad; ++o) carry[o] = q_first[o];
+    }
+    __syncthreads();
+    mlp_backward_tile<KP>(X, H1, H2, Q, w, p.lay, gs, first, tc);
+    first = false;
+  }
+  // ---- per-CTA loss / filled sums (fixed-order tree: deterministic) ----------------------------------------------
+  __syncthreads();
+  float* red = Q;
+  red[t] = loss_acc; red[kMlpThreads + t] = filled_acc;
+  __syncthreads();
+  for (int s = kMlpThreads / 2; s > 0; s >>= 1) {
+    if (t < s) { red[t] += red[t + s]; red[kMlpThreads + t] += red[kMlpThreads + t + s]; }
+    __syncthreads();
+  }
+  if (t == 0) { p.loss_part[2 * blockIdx.x] = red[0]; p.loss_part[2 * blockIdx.x + 1] = red[kMlpThreads]; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void grad_reduce_kernel(ReduceParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = p.n_nets * p.P;
+  if (i < n) {
+    const int net = i / p.P, j = i - net * p.P;
+    float s = 0.f;
+    for (int c = p.cta_begin[net]; c < p.cta_begin[net + 1]; ++c) s += p.scratch[(size_t)c * p.scratch_pitch + j];
+    p.grad[i] = s;
+  } else if (i < n + 2) {
+    const int which = i - n;
+    float s = 0.f;
+    for (int c = 0; c < p.n_loss_parts; ++c) s += p.loss_part[2 * c + which];
+    p.grad[i] = s;
+  }
+}
+
+// grad holds un-normalised sums followed by (loss_sum, filled_sum) -- possibly all-reduced over ranks.
+// Every CTA recomputes the global norm in the same order (bit-identical clip coefficient on every CTA and rank).
+__global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
+  __shared__ float red[256];
+  const float inv_fill = 1.f / p.grad[p.n + 1];
+  float clip = 1.f, norm = 0.f;
+  {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < p.n; i += 256) { const float g = p.grad[i] * inv_fill; s = fmaf(g, g, s); }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+    norm = sqrtf(red[0]);
+    if (p.grad_clip > 0.f) clip = fminf(p.grad_clip / (norm + 1e-6f), 1.f);  // torch.nn.utils.clip_grad_norm_
+  }
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < p.n) {
+    const float g = p.grad[i] * inv_fill * clip;
+    float m = p.m[i], v = p.v[i], th = p.theta[i];
+    m = m + (g - m) * (1.f - p.beta1);                       // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * p.beta2 + g * g * (1.f - p.beta2);               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / p.bc2_sqrt + p.eps;
+    th = th - (p.lr / p.bc1) * (m / denom);
+    p.m[i] = m; p.v[i] = v; p.theta[i] = th;
+    if (p.target_mode == 1) p.theta_tgt[i] = th;
+    else if (p.target_mode == 2) p.theta_tgt[i] = (1.f - p.tau) * p.theta_tgt[i] + p.tau * th;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.loss_out) { p.loss_out[0] = p.grad[p.n] * inv_fill; p.loss_out[1] = norm; }
+}
+
+// ---- launchers ------------------------------------------------------------------------------------------------
+int learner_kernels_init(int in_dim) {
+  MARL_REQUIRE(in_dim >= 1 && in_dim <= 16, "learner kernels: observation width %d not supported yet (1..16)", in_dim);
+  MARL_CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)forward_smem_bytes<16>()));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(dqn_train_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
+  return MARL_OK;
+}
+
+int launch_mlp_forward(const FwdParams& p, cudaStream_t st) {
+  mlp_forward_kernel<16><<<p.plan.cta_begin[p.plan.n_nets], kMlpThreads, forward_smem_bytes<16>(), st>>>(p);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+int launch_dqn_train(const DqnTrainParams& p, cudaStream_t st) {
+  dqn_train_kernel<16><<<p.plan.cta_begin[p.plan.n_nets], kMlpThreads, train_smem_bytes<16>(), st>>>(p);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
+  const int n = p.n_nets * p.P + 2;
+  grad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+int launch_adam(const AdamParams& p, cudaStream_t st) {
+  adam_kernel<<<(p.n + 255) / 256, 256, 0, st>>>(p);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+}  // namespace marl

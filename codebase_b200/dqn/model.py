@@ -1,0 +1,220 @@
+"""IDQN / VDN learners on the B200 path -- drop-in for marlbase/dqn/model.py (QNetwork 14-196, VDNetwork 199-269).
+
+Same constructor signature and Hydra `_target_` role (configs/algorithm/idqn.yaml:6-14, vdn.yaml:11-13), same
+`state_dict()` key names (`critic.independent.{i}.network.{0,2,4}.{weight,bias}`, `target.…`; shared:
+`critic.networks.{k}.…`) so checkpoints interchange with the reference's eval.py.  All arithmetic runs in
+libmarlb200.so (marl_dqn_*); torch is used for parameter initialisation (nn.init on the host, once) and as the
+owner of device buffers.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+from ..lbf import TrajStore
+
+HIDDEN = 128
+
+
+def _dim(space) -> int:
+    """gymnasium.spaces.flatdim for the two space kinds the reference uses (dqn/model.py:32-33)."""
+    if getattr(space, "n", None) is not None:
+        return int(space.n)
+    return int(np.prod(space.shape))
+
+
+def sharing_to_nets(parameter_sharing, n_agents):
+    """utils/models.py:189-196: True -> one network, False -> one per agent, list -> seps indices (renumbered densely)."""
+    if parameter_sharing is True:
+        return [0] * n_agents
+    if parameter_sharing is False or parameter_sharing is None:
+        return list(range(n_agents))
+    order = []
+    for i in parameter_sharing:
+        if i not in order:
+            order.append(i)
+    return [order.index(i) for i in parameter_sharing]
+
+
+def init_flat_params(n_nets, in_dim, out_dim, use_orthogonal_init=True):
+    """utils/models.py:8-11,35-44 (host side, once): nn.Linear default init, optionally orthogonal(gain sqrt 2) + zero bias."""
+    parts = []
+    for _ in range(n_nets):
+        for o, i in ((HIDDEN, in_dim), (HIDDEN, HIDDEN), (out_dim, HIDDEN)):
+            lin = torch.nn.Linear(i, o)
+            if use_orthogonal_init:
+                torch.nn.init.orthogonal_(lin.weight.data, gain=math.sqrt(2))
+                torch.nn.init.constant_(lin.bias.data, 0)
+            parts += [lin.weight.data.reshape(-1), lin.bias.data.reshape(-1)]
+    return torch.cat(parts).float()
+
+
+def flat_to_state_dict(flat, prefix, n_nets, in_dim, out_dim):
+    sd, o = OrderedDict(), 0
+    for k in range(n_nets):
+        for layer, shape in ((0, (HIDDEN, in_dim)), (2, (HIDDEN, HIDDEN)), (4, (out_dim, HIDDEN))):
+            n = shape[0] * shape[1]
+            sd[f"{prefix}.{k}.network.{layer}.weight"] = flat[o:o + n].view(*shape).clone()
+            o += n
+            sd[f"{prefix}.{k}.network.{layer}.bias"] = flat[o:o + shape[0]].clone()
+            o += shape[0]
+    return sd
+
+
+def state_dict_to_flat(sd, prefix, n_nets):
+    parts = []
+    for k in range(n_nets):
+        for layer in (0, 2, 4):
+            parts += [sd[f"{prefix}.{k}.network.{layer}.weight"].reshape(-1), sd[f"{prefix}.{k}.network.{layer}.bias"].reshape(-1)]
+    return torch.cat([p.float() for p in parts])
+
+
+class QNetwork:
+    mixer = 0
+
+    def __init__(self, obs_space, action_space, cfg, layers, parameter_sharing, use_rnn, use_orthogonal_init, device, max_batch=None, max_episode_length=None):
+        if use_rnn:
+            raise NotImplementedError("use_rnn=True (GRU) is out of scope of the B200 hot path (every shipped config has use_rnn: False)")
+        if list(layers) != [HIDDEN, HIDDEN]:
+            raise NotImplementedError(f"layers={list(layers)}: the fused kernels implement the shipped [128, 128] MLP only")
+        if getattr(cfg, "standardise_returns", False):
+            raise NotImplementedError("standardise_returns is not implemented on the B200 path (default False in every shipped config)")
+        opt = getattr(cfg, "optimizer", "Adam")
+        if (opt if isinstance(opt, str) else opt.__name__) != "Adam":
+            raise NotImplementedError("only optimizer=Adam is implemented")
+        if not torch.cuda.is_available() or not str(device).startswith("cuda"):
+            raise nat.NativeError("the B200 learners need algorithm.model.device=cuda (no CPU fallback)")
+        self.device = torch.device(device if ":" in str(device) else f"cuda:{torch.cuda.current_device()}")
+        self.n_agents = len(obs_space)
+        obs_dims, act_dims = [_dim(o) for o in obs_space], [_dim(a) for a in action_space]
+        if len(set(obs_dims)) != 1 or len(set(act_dims)) != 1:
+            raise NotImplementedError("agents with different observation / action sizes are not implemented")
+        self.in_dim, self.n_actions = obs_dims[0], act_dims[0]
+        self.action_space = action_space
+        self.agent_net = sharing_to_nets(parameter_sharing, self.n_agents)
+        self.n_nets = max(self.agent_net) + 1
+        self._kind = "independent" if not parameter_sharing else "networks"
+        self.gamma, self.grad_clip, self.double_q = float(cfg.gamma), cfg.grad_clip, bool(cfg.double_q)
+        self.target_update_interval_or_tau = float(cfg.target_update_interval_or_tau)
+        self.max_batch = int(max_batch or getattr(cfg, "batch_size", 1024))
+        self.max_T = int(max_episode_length or getattr(cfg, "max_episode_length", 0) or 500)
+        self._lib = nat.lib()
+        mcfg = nat.MlpCfg(self.n_agents, self.n_nets, (C.c_int32 * 32)(*self.agent_net), self.in_dim, HIDDEN, self.n_actions)
+        hp = nat.DqnHP(float(cfg.lr), self.gamma, float(self.grad_clip or 0.0), int(self.double_q), self.target_update_interval_or_tau,
+                       0.9, 0.999, 1e-8, self.mixer)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.marl_dqn_create(C.byref(mcfg), C.byref(hp), C.c_int32(self.max_batch), C.c_int32(self.max_T), C.c_int32(self.device.index),
+                                                C.byref(self._h)), "marl_dqn_create")
+        ptrs = [C.c_void_p() for _ in range(5)]
+        n = C.c_int64()
+        nat.check(self._lib.marl_dqn_param_ptrs(self._h, *[C.byref(p) for p in ptrs], C.byref(n)), "marl_dqn_param_ptrs")
+        self.n_params = int(n.value)
+        self.theta, self.theta_tgt, self.adam_m, self.adam_v = [nat.device_view(p.value, self.n_params, self.device) for p in ptrs[:4]]
+        self.grad = nat.device_view(ptrs[4].value, self.n_params + 2, self.device)  # + (loss numerator, filled count)
+        self.theta.copy_(init_flat_params(self.n_nets, self.in_dim, self.n_actions, use_orthogonal_init))
+        self.hard_update()
+        self._metrics = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._idx = torch.zeros(self.max_batch, dtype=torch.int32, device=self.device)
+
+    # ---- reference API ------------------------------------------------------------------------------------------
+    def init_hiddens(self, batch_size):
+        return [None] * self.n_agents
+
+    def q_values(self, obs: torch.Tensor, target: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Network pass of model.act (dqn/model.py:96-99) for E envs: obs f32[E,N,D] -> q f32[E,N,A]."""
+        E = obs.shape[0]
+        if out is None:
+            out = torch.empty(E, self.n_agents, self.n_actions, dtype=torch.float32, device=self.device)
+        nat.check(self._lib.marl_dqn_forward(self._h, nat.ptr(obs), C.c_int32(E), C.c_int32(int(target)), nat.ptr(out), nat.stream_ptr()), "marl_dqn_forward")
+        return out
+
+    def act(self, inputs, hiddens, epsilon, action_masks=None):
+        """dqn/model.py:94-116 for API parity (single env or a stack of envs).  The training / evaluation loops use the fused
+        marl_lbf_rollout_step instead, which draws exploration from the Philox stream inside the env kernel."""
+        if action_masks is not None:
+            raise NotImplementedError("action masks only exist for smaclite in the reference (out of scope)")
+        obs = torch.as_tensor(np.stack([np.asarray(i, np.float32) for i in inputs], 0), device=self.device)
+        obs = obs.view(self.n_agents, -1, self.in_dim).transpose(0, 1).contiguous()
+        q = self.q_values(obs)
+        if epsilon > float(torch.rand((), device="cpu")):
+            actions = torch.randint(0, self.n_actions, (obs.shape[0], self.n_agents))
+        else:
+            actions = q.argmax(-1).cpu()
+        return (actions[0].tolist() if actions.shape[0] == 1 else actions.T.tolist()), hiddens
+
+    def update_from_store(self, traj: TrajStore, idx: torch.Tensor):
+        """QNetwork.update on episodes `idx` (int32 device tensor) of a device trajectory store."""
+        nat.check(self._lib.marl_dqn_update(self._h, traj.ref(), nat.ptr(idx), C.c_int32(idx.numel()), nat.ptr(self._metrics), nat.stream_ptr()), "marl_dqn_update")
+        return self._metrics
+
+    def update_grads(self, traj: TrajStore, idx: torch.Tensor):
+        nat.check(self._lib.marl_dqn_update_grads(self._h, traj.ref(), nat.ptr(idx), C.c_int32(idx.numel()), nat.stream_ptr()), "marl_dqn_update_grads")
+
+    def update_apply(self):
+        nat.check(self._lib.marl_dqn_update_apply(self._h, nat.ptr(self._metrics), nat.stream_ptr()), "marl_dqn_update_apply")
+        return self._metrics
+
+    def update_n(self, traj: TrajStore, batch_size: int, n_valid: int, seed: int, first_update_idx: int, n_updates: int):
+        """`rb.sample(batch); model.update(batch)` n times on device (dqn/train.py:308-311)."""
+        nat.check(self._lib.marl_dqn_update_n(self._h, traj.ref(), C.c_int32(batch_size), C.c_int32(n_valid), C.c_uint64(seed & (2**64 - 1)),
+                                              C.c_uint64(first_update_idx), C.c_int32(n_updates), nat.ptr(self._metrics), nat.stream_ptr()), "marl_dqn_update_n")
+        return self._metrics
+
+    def update(self, batch):
+        """Reference signature (dqn/model.py:165-174): `batch` is the reference's Batch namedtuple (obss (N,T+1,B,obs), actions
+        (N,T,B), rewards (N,T,B), dones (T+1,B), filled (T,B)); converted to the device layout, then the native update."""
+        obss = batch.obss
+        N, T1, B, D = obss.shape
+        store = TrajStore(B, N, T1 - 1, D, self.device)
+        store.obs.copy_(obss.permute(2, 0, 1, 3))
+        store.act.copy_(batch.actions.permute(2, 0, 1))
+        store.rew.copy_(batch.rewards.permute(2, 0, 1))
+        store.done.copy_(batch.dones.permute(1, 0))
+        store.filled.copy_(batch.filled.permute(1, 0))
+        idx = torch.arange(B, dtype=torch.int32, device=self.device)
+        m = self.update_from_store(store, idx)
+        return {"loss": float(m[0].item())}
+
+    @property
+    def updates(self) -> int:
+        u = C.c_int64()
+        nat.check(self._lib.marl_dqn_counters(self._h, C.byref(u), None), "marl_dqn_counters")
+        return int(u.value)
+
+    def hard_update(self):
+        nat.check(self._lib.marl_dqn_sync_target(self._h, nat.stream_ptr()), "marl_dqn_sync_target")
+
+    def state_dict(self):
+        sd = flat_to_state_dict(self.theta.detach().cpu(), f"critic.{self._kind}", self.n_nets, self.in_dim, self.n_actions)
+        sd.update(flat_to_state_dict(self.theta_tgt.detach().cpu(), f"target.{self._kind}", self.n_nets, self.in_dim, self.n_actions))
+        return sd
+
+    def load_state_dict(self, sd):
+        self.theta.copy_(state_dict_to_flat(sd, f"critic.{self._kind}", self.n_nets))
+        self.theta_tgt.copy_(state_dict_to_flat(sd, f"target.{self._kind}", self.n_nets))
+
+    def parameters(self):
+        return [self.theta]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.marl_dqn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VDNetwork(QNetwork):
+    """marlbase/dqn/model.py:199-269: Q_tot = sum_i Q_i, reward of agent 0 (CooperativeReward makes them equal)."""
+
+    mixer = 1

@@ -135,6 +135,63 @@ int marl_lbf_rollout_step(marl_lbf* env, const float* values, const marl_rollout
                           uint8_t* trunc_out, float* final_ret_out, int32_t* final_len_out,
                           int32_t* actions_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Per-agent MLP sets and the DQN-family learner (IDQN, VDN).
+ * Replaces marlbase/dqn/model.py QNetwork (14-196) / VDNetwork (199-269) and the network containers of
+ * marlbase/utils/models.py:133-300.  Parameters are one flat float array [n_nets][P] in the reference's
+ * state_dict order per network: network.0.weight [H][in], network.0.bias [H], network.2.weight [H][H],
+ * network.2.bias [H], network.4.weight [out][H], network.4.bias [out]  (utils/models.py:35-44).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_agents, n_nets;
+  int32_t agent_net[MARL_MAX_AGENTS]; /* network of each agent: identity = independent (parameter_sharing False),
+                                         all 0 = full sharing, else the seps indices (utils/models.py:189-196) */
+  int32_t in_dim;                     /* flatdim(observation_space[i]) */
+  int32_t hidden;                     /* layers = [hidden, hidden]; 128 (idqn.yaml:8-10) */
+  int32_t out_dim;                    /* n_actions (Q / logits) or 1 (state value) */
+} marl_mlp_cfg;
+
+typedef struct {
+  float   lr;                             /* idqn.yaml:18 */
+  float   gamma;                          /* idqn.yaml:19 */
+  float   grad_clip;                      /* idqn.yaml:23, <= 0 disables clip_grad_norm_ */
+  int32_t double_q;                       /* idqn.yaml:21 */
+  float   target_update_interval_or_tau;  /* idqn.yaml:37: > 1 hard update every k updates, < 1 Polyak tau */
+  float   beta1, beta2, eps;              /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 (dqn/model.py:71) */
+  int32_t mixer;                          /* 0 = independent learners (QNetwork), 1 = VDN sum (VDNetwork) */
+} marl_dqn_hp;
+
+typedef struct marl_dqn marl_dqn;
+
+int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_batch, int32_t max_T, int32_t device,
+                    marl_dqn** out);
+int marl_dqn_destroy(marl_dqn* q);
+/* Device pointers to the flat parameter / optimiser state ([n_nets*P] floats each; grad has 2 extra floats:
+ * loss numerator and filled count).  Initialise theta through these (orthogonal init is done by the caller). */
+int marl_dqn_param_ptrs(marl_dqn* q, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad,
+                        int64_t* n_params);
+int marl_dqn_sync_target(marl_dqn* q, void* stream);        /* hard_update (dqn/model.py:195-196) */
+/* model.act's network pass (dqn/model.py:96-99) for E envs at once: obs device float[E][N][in] -> q float[E][N][out] */
+int marl_dqn_forward(marl_dqn* q, const float* obs, int32_t n_envs, int32_t use_target, float* q_out, void* stream);
+/* np.random.randint(0, len(rb), batch) (dqn/train.py:95) from the Philox stream (seed, update_idx) */
+int marl_replay_sample(uint64_t seed, uint64_t update_idx, int32_t batch, int32_t n_valid, int32_t* idx_out,
+                       void* stream);
+/* QNetwork.update (dqn/model.py:165-174) split at the point where data-parallel ranks exchange:
+ *   _grads: rb.sample gather + _compute_loss + backward  -> un-normalised gradient sums in `grad`
+ *   (caller may all-reduce grad[0 .. n_params+2) over ranks here)
+ *   _apply: / filled.sum(), clip_grad_norm_, Adam.step, updates += 1, update_target; loss_out device float[2]
+ *           = (loss, gradient norm before clipping) or NULL */
+int marl_dqn_update_grads(marl_dqn* q, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch,
+                          void* stream);
+int marl_dqn_update_apply(marl_dqn* q, float* loss_out, void* stream);
+int marl_dqn_update(marl_dqn* q, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch,
+                    float* loss_out, void* stream);
+/* `rb.sample(); model.update()` (dqn/train.py:308-311) n_updates times without returning to Python */
+int marl_dqn_update_n(marl_dqn* q, const marl_traj_view* traj, int32_t batch, int32_t n_valid, uint64_t seed,
+                      uint64_t first_update_idx, int32_t n_updates, float* loss_out, void* stream);
+int marl_dqn_counters(marl_dqn* q, int64_t* updates, int64_t* last_target_update);
+int marl_dqn_set_counters(marl_dqn* q, int64_t updates, int64_t last_target_update);
+
 #ifdef __cplusplus
 }
 #endif
