@@ -116,7 +116,10 @@ struct marl_dqn {
   int32_t* idx = nullptr;
   int64_t updates = 0, last_target_update = 0;
   RowPlan train_plan; int n_loss_parts = 0;
+  // optional CUDA-event timing of the training kernel (bench.py's roofline leg)
+  bool timing = false; std::vector<cudaEvent_t> ev; int ev_used = 0;
 };
+static const int kTimingPairs = 1024;
 
 static int dqn_alloc(float** p, size_t n_floats) {
   cudaError_t e = cudaMalloc((void**)p, n_floats * sizeof(float));
@@ -174,6 +177,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
   cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->idx);
+  for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
 }
@@ -238,7 +242,10 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   }
   DqnTrainParams tp; tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext;
   tp.gamma = h->hp.gamma; tp.double_q = h->hp.double_q; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch; tp.loss_part = loss_part;
+  const bool rec = h->timing && h->ev_used < kTimingPairs;
+  if (rec) cudaEventRecord(h->ev[2 * h->ev_used], st);
   if (int rc = launch_dqn_train(tp, st)) return rc;
+  if (rec) { cudaEventRecord(h->ev[2 * h->ev_used + 1], st); h->ev_used += 1; }
   ReduceParams rp; rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->ns.n_nets; rp.P = h->ns.lay.P; rp.scratch_pitch = h->scratch_pitch;
   memcpy(rp.cta_begin, plan.cta_begin, sizeof(rp.cta_begin));
   rp.n_loss_parts = n_loss_parts; rp.grad = h->grad;
@@ -277,6 +284,28 @@ int marl_dqn_update_n(marl_dqn* h, const marl_traj_view* traj, int32_t batch, in
     if (int rc = marl_replay_sample(seed, first_update_idx + (uint64_t)u, batch, n_valid, h->idx, stream)) return rc;
     if (int rc = marl_dqn_update(h, traj, h->idx, batch, loss_out, stream)) return rc;
   }
+  return MARL_OK;
+}
+
+/* CUDA-event timing of dqn_train_kernel launches: enable=1 starts recording (first 1024 launches), enable=0 stops, synchronises
+ * the recorded events and returns their summed duration and count. */
+int marl_dqn_timing(marl_dqn* h, int32_t enable, float* total_ms, int32_t* count) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_timing: NULL handle");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  if (enable) {
+    if (h->ev.empty()) { h->ev.resize(2 * kTimingPairs); for (auto& e : h->ev) MARL_CUDA_TRY(cudaEventCreate(&e)); }
+    h->ev_used = 0; h->timing = true;
+    return MARL_OK;
+  }
+  h->timing = false;
+  float tot = 0.f;
+  for (int i = 0; i < h->ev_used; ++i) {
+    MARL_CUDA_TRY(cudaEventSynchronize(h->ev[2 * i + 1]));
+    float ms = 0.f; MARL_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (count) *count = h->ev_used;
   return MARL_OK;
 }
 

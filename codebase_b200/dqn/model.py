@@ -181,6 +181,12 @@ class QNetwork:
         m = self.update_from_store(store, idx)
         return {"loss": float(m[0].item())}
 
+    def timing(self, enable: bool):
+        """CUDA-event timing of the training kernel: timing(True) starts, timing(False) -> (total_ms, launches)."""
+        ms, n = C.c_float(), C.c_int32()
+        nat.check(self._lib.marl_dqn_timing(self._h, C.c_int32(int(enable)), C.byref(ms), C.byref(n)), "marl_dqn_timing")
+        return float(ms.value), int(n.value)
+
     @property
     def updates(self) -> int:
         u = C.c_int64()

@@ -190,6 +190,8 @@ int marl_dqn_update(marl_dqn* q, const marl_traj_view* traj, const int32_t* epis
 int marl_dqn_update_n(marl_dqn* q, const marl_traj_view* traj, int32_t batch, int32_t n_valid, uint64_t seed,
                       uint64_t first_update_idx, int32_t n_updates, float* loss_out, void* stream);
 int marl_dqn_counters(marl_dqn* q, int64_t* updates, int64_t* last_target_update);
+/* measurement hook (bench.py roofline leg): CUDA-event time of the training-kernel launches between enable=1 and enable=0 */
+int marl_dqn_timing(marl_dqn* q, int32_t enable, float* total_ms, int32_t* count);
 int marl_dqn_set_counters(marl_dqn* q, int64_t updates, int64_t last_target_update);
 
 #ifdef __cplusplus

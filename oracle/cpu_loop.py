@@ -1,0 +1,92 @@
+"""The reference's IDQN training loop restated on the CPU: marlbase/dqn/train.py:298-311 (collect one episode with one
+env -> one sampled update), marlbase/dqn/model.py:94-116 (act: per-agent forward on a (1,1,obs) tensor, one
+`random.random()` exploration test per step), 1 torch thread as marlbase/run.py:29 mandates.
+
+TEST / MEASUREMENT INFRASTRUCTURE ONLY: this is what bench.py times as `cpu_baseline` and as `--impl reference`
+(kind "port": /root/reference and the third-party `lbforaging` package do not exist on the GPU box).  The env is the
+pure-Python restatement (oracle/lbf_ref.py), which has the same cost structure as upstream lbforaging (Python objects +
+small numpy arrays); the learner is oracle/learner_ref.py (PyTorch CPU autograd + the Adam arithmetic of torch.optim).
+"""
+from __future__ import annotations
+
+import random
+import time
+
+import numpy as np
+import torch
+
+from . import learner_ref as lr
+from .lbf_ref import LBFConfig, WrappedForaging
+
+
+class CpuIdqn:
+    def __init__(self, cfg: LBFConfig, batch_size: int, buffer_size: int = 10000, seed: int = 0, hp: lr.DqnHP | None = None):
+        torch.set_num_threads(1)  # run.py:29
+        torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
+        self.cfg, self.B, self.hp = cfg, batch_size, hp or lr.DqnHP()
+        self.env = WrappedForaging(cfg, seed)
+        self.N, self.D, self.A, self.T = cfg.n_agents, cfg.obs_dim, 6, cfg.time_limit
+        theta = lr.init_flat(self.N, self.D, self.A)
+        self.st = lr.DqnState(theta, theta.clone(), list(range(self.N)), self.D, self.A)
+        self.rb = lr.ReplayRef(buffer_size, self.N, self.T, self.D)
+        self.P = lr.net_size(self.D, self.A)
+
+    def act(self, obss, epsilon):
+        with torch.no_grad():  # the reference runs the forward even when it then explores (dqn/model.py:95-99,105)
+            inputs = [torch.tensor(o).view(1, 1, -1) for o in obss]
+            values = lr.agents_forward(self.st.theta, self.st.agent_net, inputs, self.D, self.A)
+        if epsilon > random.random():
+            return [random.randrange(self.A) for _ in range(self.N)]
+        return [v.argmax(-1).squeeze().item() for v in values]
+
+    def collect_episode(self, epsilon, use_network=True):
+        obss, _ = self.env.reset()
+        self.rb.init_episode(obss)
+        done, t = False, 0
+        while not done:
+            actions = self.act(obss, epsilon) if use_network else [random.randrange(self.A) for _ in range(self.N)]
+            obss, rews, d, trunc, _ = self.env.step(actions)
+            done = d or trunc
+            self.rb.add(obss, actions, rews, done)
+            t += 1
+        return t
+
+    def update(self):
+        idx = np.random.randint(0, len(self.rb), size=self.B)  # dqn/train.py:95
+        return lr.dqn_update(self.st, lr.batch_from_store(self.rb.store, idx), self.hp)["loss"]
+
+    def prefill(self, n_episodes):
+        for _ in range(n_episodes):
+            self.collect_episode(1.0, use_network=False)
+
+    def run(self, n_episodes, epsilon=0.5):
+        """n_episodes iterations of `collect one episode; one update` -> (env_steps, seconds)."""
+        steps, t0 = 0, time.perf_counter()
+        for _ in range(n_episodes):
+            steps += self.collect_episode(epsilon)
+            self.update()
+        return steps, time.perf_counter() - t0
+
+
+def _worker(args):
+    cfg_kw, batch_size, seed, prefill, n_episodes, n_rounds = args
+    loop = CpuIdqn(LBFConfig(**cfg_kw), batch_size, seed=seed)
+    loop.prefill(prefill)
+    out = []
+    for _ in range(n_rounds):
+        out.append(loop.run(n_episodes))
+    return out
+
+
+def run_parallel(cfg_kw, batch_size, n_procs, prefill, n_episodes, n_rounds, pool=None):
+    """`n_procs` independent single-thread copies of the reference loop (one per host core); returns per-round
+    (total env steps, max seconds over workers)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    with ctx.Pool(n_procs) as p:
+        res = p.map(_worker, [(cfg_kw, batch_size, 1000 + i, prefill, n_episodes, n_rounds) for i in range(n_procs)])
+    rounds = []
+    for r in range(n_rounds):
+        rounds.append((sum(w[r][0] for w in res), max(w[r][1] for w in res)))
+    return rounds
