@@ -166,7 +166,7 @@ def run_b200(args):
     h_rew = torch.empty_like(nat_env.rew, device="cpu").pin_memory()
     h_done = torch.empty_like(nat_env.done, device="cpu").pin_memory()
     h_trunc = torch.empty_like(nat_env.trunc, device="cpu").pin_memory()
-    h_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    h_loss = torch.empty(6, dtype=torch.float32).pin_memory()
     d_obs_in = torch.empty_like(nat_env.obs)
 
     def do_updates():
@@ -260,7 +260,7 @@ def run_b200(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     train_bytes = B * 3421 + 7 * 4 * model.n_params       # gathered episodes + parameter / Adam traffic
     achieved = train_flop / train_avg_s / 1e12 if train_n else None
-    roofline = {"bound": "fp32-fma", "kernel": "dqn_train_kernel<16>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "fp32-fma", "kernel": "train_kernel<16, kHeadDqn>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": (achieved / fp32_peak) if achieved else None, "traffic": None,
                 "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz median SM clock sampled during the run (MEASURED_PEAKS.json holds no FP32 figure)",
                 "launch_us": 1e6 * train_avg_s, "launches_timed": train_n, "flop_per_launch": train_flop,

@@ -60,6 +60,12 @@ class DqnHP(C.Structure):
                 ("mixer", C.c_int32)]
 
 
+class A2cHP(C.Structure):
+    _fields_ = [("lr", C.c_float), ("gamma", C.c_float), ("grad_clip", C.c_float), ("n_steps", C.c_int32), ("entropy_coef", C.c_float),
+                ("value_loss_coef", C.c_float), ("target_update_interval_or_tau", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float)]
+
+
 class _DevArray:
     """Zero-copy torch view of library-owned device memory through the CUDA array interface."""
 

@@ -23,7 +23,7 @@ struct VdnTdParams {
   const float* q; const float* tq;  // [N][B][T+1][A]
   TrajView traj; const int32_t* idx; int B, N, A; float gamma; int double_q;
   float* td;         // [B][T] = 2 * delta * filled
-  float* loss_part;  // [gridDim][2]
+  float* loss_part;  // [gridDim][4]
 };
 
 __global__ void __launch_bounds__(256) vdn_td_kernel(VdnTdParams p) {
@@ -60,45 +60,7 @@ __global__ void __launch_bounds__(256) vdn_td_kernel(VdnTdParams p) {
     if (threadIdx.x < s) { red[threadIdx.x] += red[threadIdx.x + s]; red[256 + threadIdx.x] += red[256 + threadIdx.x + s]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { p.loss_part[2 * blockIdx.x] = red[0]; p.loss_part[2 * blockIdx.x + 1] = red[256]; }
-}
-
-// ---- host-side planning -----------------------------------------------------------------------------------------
-struct NetSet {
-  int n_agents = 0, n_nets = 0, in = 0, out = 0;
-  int agent_net[MARL_MAX_AGENTS];
-  NetLayout lay;
-};
-
-// Split `n_cta_max` CTAs over the networks in proportion to their row counts; every CTA gets >= min_units units.
-static RowPlan make_plan(const NetSet& ns, int units_per_agent, int unit_rows, int n_cta_max, int min_units) {
-  RowPlan p; memset(&p, 0, sizeof(p));
-  p.n_nets = ns.n_nets; p.unit_rows = unit_rows; p.units_per_agent = units_per_agent;
-  int s = 0;
-  for (int k = 0; k < ns.n_nets; ++k) {
-    p.slot_begin[k] = s;
-    for (int a = 0; a < ns.n_agents; ++a) if (ns.agent_net[a] == k) p.slot_agent[s++] = a;
-  }
-  p.slot_begin[ns.n_nets] = s;
-  long long total = (long long)ns.n_agents * units_per_agent;
-  int c = 0;
-  for (int k = 0; k < ns.n_nets; ++k) {
-    const long long units = (long long)(p.slot_begin[k + 1] - p.slot_begin[k]) * units_per_agent;
-    long long want = (long long)n_cta_max * units / (total > 0 ? total : 1);
-    const long long cap = (units + min_units - 1) / min_units;
-    if (want > cap) want = cap;
-    if (want < 1) want = 1;
-    p.cta_begin[k] = c;
-    c += (int)want;
-  }
-  p.cta_begin[ns.n_nets] = c;
-  return p;
-}
-
-static TrajView to_view(const marl_traj_view* t) {
-  TrajView v; v.obs = t->obs; v.act = t->act; v.rew = t->rew; v.done = t->done; v.filled = t->filled;
-  v.capacity = t->capacity; v.N = t->n_agents; v.T = t->T; v.D = t->obs_dim;
-  return v;
+  if (threadIdx.x == 0) { p.loss_part[4 * blockIdx.x] = red[0]; p.loss_part[4 * blockIdx.x + 1] = red[256]; p.loss_part[4 * blockIdx.x + 2] = 0.f; p.loss_part[4 * blockIdx.x + 3] = 0.f; }
 }
 
 }  // namespace marl
@@ -121,18 +83,7 @@ struct marl_dqn {
 };
 static const int kTimingPairs = 1024;
 
-static int dqn_alloc(float** p, size_t n_floats) {
-  cudaError_t e = cudaMalloc((void**)p, n_floats * sizeof(float));
-  if (e == cudaSuccess) e = cudaMemset(*p, 0, n_floats * sizeof(float));
-  if (e != cudaSuccess) { set_error("marl_dqn: cudaMalloc(%zu floats) failed: %s", n_floats, cudaGetErrorString(e)); return MARL_ENOMEM; }
-  return MARL_OK;
-}
-
-static int launch_forward(const NetSet& ns, int n_sm, const RowPlan& plan, const RowSource& src, const float* theta, float* out, cudaStream_t st) {
-  FwdParams fp; fp.plan = plan; fp.src = src; fp.theta = theta; fp.lay = ns.lay; fp.out = out;
-  (void)n_sm;
-  return launch_mlp_forward(fp, st);
-}
+static int dqn_alloc(float** p, size_t n_floats) { return dev_alloc_zero(p, n_floats); }
 
 extern "C" {
 
@@ -159,11 +110,11 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   const size_t rows = (size_t)cfg->n_agents * max_batch * (max_T + 1);
   int rc = 0;
   rc |= dqn_alloc(&h->theta, h->n_params); rc |= dqn_alloc(&h->theta_tgt, h->n_params);
-  rc |= dqn_alloc(&h->m, h->n_params); rc |= dqn_alloc(&h->v, h->n_params); rc |= dqn_alloc(&h->grad, h->n_params + 2);
+  rc |= dqn_alloc(&h->m, h->n_params); rc |= dqn_alloc(&h->v, h->n_params); rc |= dqn_alloc(&h->grad, h->n_params + 4);
   rc |= dqn_alloc(&h->scratch, (size_t)h->n_sm * h->scratch_pitch);
-  rc |= dqn_alloc(&h->loss_part, 2 * ((size_t)h->n_sm + (size_t)max_batch * max_T / 256 + 2));
+  rc |= dqn_alloc(&h->loss_part, 4 * ((size_t)h->n_sm + (size_t)max_batch * max_T / 256 + 2));
   rc |= dqn_alloc(&h->tq, rows * cfg->out_dim);
-  rc |= dqn_alloc(&h->loss_dev, 2);
+  rc |= dqn_alloc(&h->loss_dev, 8);
   if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
   if (rc) { marl_dqn_destroy(h); return MARL_ENOMEM; }
@@ -202,7 +153,7 @@ int marl_dqn_forward(marl_dqn* h, const float* obs, int32_t n_envs, int32_t use_
   const RowPlan plan = make_plan(h->ns, n_envs, 1, h->n_sm, 32);
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 0; src.dense = obs; src.E = n_envs; src.N = h->ns.n_agents; src.D = h->ns.in;
-  return launch_forward(h->ns, h->n_sm, plan, src, use_target ? h->theta_tgt : h->theta, q_out, (cudaStream_t)stream);
+  return launch_forward(h->ns, plan, src, use_target ? h->theta_tgt : h->theta, q_out, (cudaStream_t)stream);
 }
 
 int marl_replay_sample(uint64_t seed, uint64_t update_idx, int32_t batch, int32_t n_valid, int32_t* idx_out, void* stream) {
@@ -225,30 +176,31 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 1; src.traj = to_view(traj); src.idx = episode_idx; src.N = h->ns.n_agents; src.D = h->ns.in;
   // target network on every gathered row (dqn/model.py:132-134)
-  if (int rc = launch_forward(h->ns, h->n_sm, plan, src, h->theta_tgt, h->tq, st)) return rc;
+  if (int rc = launch_forward(h->ns, plan, src, h->theta_tgt, h->tq, st)) return rc;
   int n_loss_parts = plan.cta_begin[plan.n_nets];
   const float* td_ext = nullptr;
   float* loss_part = h->loss_part;
   if (h->hp.mixer == 1) {  // VDN: online Q-values of all agents first, then the agent-summed TD error
-    if (int rc = launch_forward(h->ns, h->n_sm, plan, src, h->theta, h->q_all, st)) return rc;
+    if (int rc = launch_forward(h->ns, plan, src, h->theta, h->q_all, st)) return rc;
     VdnTdParams vp; vp.q = h->q_all; vp.tq = h->tq; vp.traj = src.traj; vp.idx = episode_idx; vp.B = batch; vp.N = h->ns.n_agents; vp.A = h->ns.out;
     vp.gamma = h->hp.gamma; vp.double_q = h->hp.double_q; vp.td = h->td;
     const int vb = (batch * T + 255) / 256;
-    vp.loss_part = h->loss_part + 2 * (size_t)n_loss_parts;  // the train kernel's parts read as zero in this mode
+    vp.loss_part = h->loss_part + 4 * (size_t)n_loss_parts;  // the train kernel's parts read as zero in this mode
     vdn_td_kernel<<<vb, 256, 0, st>>>(vp);
     MARL_CUDA_TRY(cudaGetLastError());
     n_loss_parts += vb;
     td_ext = h->td;
   }
-  DqnTrainParams tp; tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext;
+  TrainParams tp; memset(&tp, 0, sizeof(tp));
+  tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext;
   tp.gamma = h->hp.gamma; tp.double_q = h->hp.double_q; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch; tp.loss_part = loss_part;
   const bool rec = h->timing && h->ev_used < kTimingPairs;
   if (rec) cudaEventRecord(h->ev[2 * h->ev_used], st);
-  if (int rc = launch_dqn_train(tp, st)) return rc;
+  if (int rc = launch_train(tp, kHeadDqn, st)) return rc;
   if (rec) { cudaEventRecord(h->ev[2 * h->ev_used + 1], st); h->ev_used += 1; }
   ReduceParams rp; rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->ns.n_nets; rp.P = h->ns.lay.P; rp.scratch_pitch = h->scratch_pitch;
   memcpy(rp.cta_begin, plan.cta_begin, sizeof(rp.cta_begin));
-  rp.n_loss_parts = n_loss_parts; rp.grad = h->grad;
+  rp.n_loss_parts = n_loss_parts; rp.grad = h->grad; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0;
   return launch_grad_reduce(rp, st);
 }
 
@@ -262,7 +214,7 @@ int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   ap.bc2_sqrt = (float)sqrt(1.0 - pow((double)h->hp.beta2, (double)h->updates));
   // update_target (dqn/model.py:176-185)
   const float tu = h->hp.target_update_interval_or_tau;
-  ap.target_mode = 0; ap.tau = tu;
+  ap.target_mode = 0; ap.tau = tu; ap.tgt_begin = 0; ap.tgt_n = (int)h->n_params;
   if (tu > 1.0f && (float)(h->updates - h->last_target_update) >= tu) { ap.target_mode = 1; h->last_target_update = h->updates; }
   else if (tu < 1.0f) ap.target_mode = 2;
   ap.loss_out = loss_out ? loss_out : h->loss_dev;

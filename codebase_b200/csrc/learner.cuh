@@ -2,6 +2,7 @@
 // forward+loss-head+backward training pass, deterministic gradient reduction, clip + Adam + target update.
 #pragma once
 #include "mlp.cuh"
+#include <string.h>
 
 namespace marl {
 
@@ -73,35 +74,51 @@ struct FwdParams {
   float* out;           // mode 0: [E][N][out]; mode 1: [N][B][T+1][out]
 };
 
-struct DqnTrainParams {
+// Loss heads of the fused training kernel (what happens between the forward and the backward of a tile).
+enum TrainHead { kHeadDqn = 0, kHeadA2cCritic = 1, kHeadA2cActor = 2 };
+
+struct TrainParams {
   RowPlan plan; RowSource src;
   const float* theta; NetLayout lay;
+  float* scratch;         // [gridDim][pitch] per-CTA gradient sums (un-normalised); pitch = P rounded up to 4 floats
+  int scratch_pitch;
+  float* loss_part;       // [gridDim][4] per-CTA loss statistics, meaning depends on the head (see below)
+  // kHeadDqn: parts = (sum delta^2*filled, sum filled on agent 0, 0, 0)
   const float* tq;        // target-net Q-values of every gathered row, [N][B][T+1][out] (from the forward kernel)
   const float* td_ext;    // VDN: precomputed 2*delta*filled per (b, t), [B][T]; NULL for independent learners
   float gamma; int double_q;
-  float* scratch;         // [gridDim][pitch] per-CTA gradient sums (un-normalised); pitch = P rounded up to 4 floats
-  int scratch_pitch;
-  float* loss_part;       // [gridDim][2] = (sum delta^2*filled, sum filled counted on agent 0 only)
+  // kHeadA2cCritic: parts = (0, sum filled on agent 0, 0, sum adv^2*filled); writes adv = returns - V
+  const float* returns;   // [N][B][T] n-step returns
+  float* adv_out;         // [N][B][T]
+  float value_coef;
+  // kHeadA2cActor: parts = (sum -logp*adv*filled, 0, sum entropy*filled, 0)
+  const float* adv;       // [N][B][T]
+  float entropy_coef;
 };
 
 struct ReduceParams {
   const float* scratch; const float* loss_part; int n_nets; int cta_begin[MARL_MAX_AGENTS + 1]; int P; int scratch_pitch;
   int n_loss_parts;
-  float* grad;  // [n_nets*P + 2]: gradient sums, then loss_sum, filled_sum
+  float* grad;       // [n_nets*P] gradient sums of this network set
+  float* stats;      // [4] sums of the loss parts (NULL: skip)
+  int stats_accumulate;  // add to stats instead of overwriting (second pass of an actor-critic update)
 };
 
 struct AdamParams {
-  float* theta; float* theta_tgt; float* m; float* v; const float* grad; int n;  // n = n_nets*P trainable floats
+  float* theta; float* theta_tgt; float* m; float* v;
+  const float* grad;   // [n] gradient sums followed by 4 statistics: (loss numerator, filled count, aux0, aux1)
+  int n;               // trainable floats
+  int tgt_begin, tgt_n;  // theta[tgt_begin .. tgt_begin+tgt_n) is mirrored by theta_tgt[0 .. tgt_n)
   float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_clip;  // grad_clip <= 0: off
   int target_mode;  // 0 none, 1 hard copy, 2 polyak
   float tau;
-  float* loss_out;  // [2]: mean loss, grad norm
+  float* loss_out;  // [6]: stats[0]/filled, grad norm, stats[2]/filled, stats[3]/filled, filled, 0
 };
 
 // host-side launchers (defined next to the kernels in learner_kernels.cu); return MARL_* codes
 int learner_kernels_init(int in_dim);                       // opt in to > 48 KB dynamic shared memory
 int launch_mlp_forward(const FwdParams& p, cudaStream_t st);
-int launch_dqn_train(const DqnTrainParams& p, cudaStream_t st);
+int launch_train(const TrainParams& p, int head, cudaStream_t st);
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
@@ -109,5 +126,74 @@ template <int KP>
 constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + kTileRows * KP + 2 * kTileRows * kHidden + kTileRows * kOutPad); }
 template <int KP>
 constexpr size_t train_smem_bytes() { return forward_smem_bytes<KP>() + sizeof(float) * 16; }
+
+// ---- host-side planning -----------------------------------------------------------------------------------------
+struct NetSet {
+  int n_agents = 0, n_nets = 0, in = 0, out = 0;
+  int agent_net[MARL_MAX_AGENTS];
+  NetLayout lay;
+};
+
+// Split `n_cta_max` CTAs over the networks in proportion to their row counts; every CTA gets >= min_units units.
+inline RowPlan make_plan(const NetSet& ns, int units_per_agent, int unit_rows, int n_cta_max, int min_units) {
+  RowPlan p; memset(&p, 0, sizeof(p));
+  p.n_nets = ns.n_nets; p.unit_rows = unit_rows; p.units_per_agent = units_per_agent;
+  int s = 0;
+  for (int k = 0; k < ns.n_nets; ++k) {
+    p.slot_begin[k] = s;
+    for (int a = 0; a < ns.n_agents; ++a) if (ns.agent_net[a] == k) p.slot_agent[s++] = a;
+  }
+  p.slot_begin[ns.n_nets] = s;
+  long long total = (long long)ns.n_agents * units_per_agent;
+  int c = 0;
+  for (int k = 0; k < ns.n_nets; ++k) {
+    const long long units = (long long)(p.slot_begin[k + 1] - p.slot_begin[k]) * units_per_agent;
+    long long want = (long long)n_cta_max * units / (total > 0 ? total : 1);
+    const long long cap = (units + min_units - 1) / min_units;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    p.cta_begin[k] = c;
+    c += (int)want;
+  }
+  p.cta_begin[ns.n_nets] = c;
+  return p;
+}
+
+inline TrajView to_view(const marl_traj_view* t) {
+  TrajView v; v.obs = t->obs; v.act = t->act; v.rew = t->rew; v.done = t->done; v.filled = t->filled;
+  v.capacity = t->capacity; v.N = t->n_agents; v.T = t->T; v.D = t->obs_dim;
+  return v;
+}
+
+
+inline int dev_alloc_zero(float** p, size_t n_floats) {
+  cudaError_t e = cudaMalloc((void**)p, n_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, n_floats * sizeof(float));
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu floats) failed: %s", n_floats, cudaGetErrorString(e)); return MARL_ENOMEM; }
+  return MARL_OK;
+}
+
+inline int launch_forward(const NetSet& ns, const RowPlan& plan, const RowSource& src, const float* theta, float* out, cudaStream_t st) {
+  FwdParams fp; fp.plan = plan; fp.src = src; fp.theta = theta; fp.lay = ns.lay; fp.out = out;
+  return launch_mlp_forward(fp, st);
+}
+
+inline int check_mlp_cfg(const marl_mlp_cfg* cfg, const char* who) {
+  MARL_REQUIRE(cfg != nullptr, "%s: NULL network config", who);
+  MARL_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= MARL_MAX_AGENTS, "%s: n_agents out of range", who);
+  MARL_REQUIRE(cfg->n_nets >= 1 && cfg->n_nets <= cfg->n_agents, "%s: n_nets out of range", who);
+  MARL_REQUIRE(cfg->hidden == kHidden, "%s: only layers=[128,128] is implemented on the B200 path (got hidden=%d)", who, cfg->hidden);
+  MARL_REQUIRE(cfg->in_dim >= 1 && cfg->in_dim <= 16, "%s: obs dim %d not supported yet (1..16)", who, cfg->in_dim);
+  MARL_REQUIRE(cfg->out_dim >= 1 && cfg->out_dim <= kOutPad, "%s: output width %d not supported (1..%d)", who, cfg->out_dim, kOutPad);
+  for (int a = 0; a < cfg->n_agents; ++a) MARL_REQUIRE(cfg->agent_net[a] >= 0 && cfg->agent_net[a] < cfg->n_nets, "%s: agent_net[%d] out of range", who, a);
+  return MARL_OK;
+}
+
+inline NetSet to_netset(const marl_mlp_cfg* cfg) {
+  NetSet ns; ns.n_agents = cfg->n_agents; ns.n_nets = cfg->n_nets; ns.in = cfg->in_dim; ns.out = cfg->out_dim;
+  memcpy(ns.agent_net, cfg->agent_net, sizeof(int) * MARL_MAX_AGENTS);
+  ns.lay = NetLayout::make(cfg->in_dim, cfg->out_dim);
+  return ns;
+}
 
 }  // namespace marl

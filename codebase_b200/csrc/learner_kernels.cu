@@ -4,7 +4,7 @@
 //                       (marlbase/dqn/model.py:99, marlbase/ac/model.py:148-149) and the target-network pass of the
 //                       learner (marlbase/dqn/model.py:132-134, marlbase/ac/model.py:190-193).  Replay gather
 //                       (marlbase/dqn/train.py:94-124) is fused into the tile load.
-//  dqn_train_kernel     QNetwork._compute_loss + loss.backward() (marlbase/dqn/model.py:118-168): gather, online
+//  train_kernel         (head DQN) QNetwork._compute_loss + loss.backward() (marlbase/dqn/model.py:118-168): gather, online
 //                       forward, double-Q TD target, MSE, masked mean numerator, full backward; every CTA keeps its
 //                       network's weights resident in shared memory and walks its episodes tile by tile.
 //  grad_reduce_kernel   deterministic sum of the per-CTA gradient partials (+ loss / filled sums).
@@ -188,30 +188,100 @@ __device__ __forceinline__ void mlp_backward_tile(const float* X, float* H1, flo
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int KP>
-__global__ void __launch_bounds__(kMlpThreads, 1) dqn_train_kernel(DqnTrainParams p) {
+// Loss heads: one thread per row of the tile.  `q` = this row's network outputs, `qn` = next row's (same episode),
+// results: dq[0..7] = dLoss/d(output) un-normalised, st[0..3] += loss statistics.
+struct RowCtx { int agent, b, tt, T, A, B; size_t ep; };
+
+__device__ __forceinline__ void head_dqn(const TrainParams& p, const RowCtx& c, const float* q, const float* qn, float (&dq)[kOutPad], float (&st)[4]) {
+  const TrajView& tv = p.src.traj;
+  const int act = tv.act[(c.ep * tv.N + c.agent) * c.T + c.tt];
+  const float filled = (float)tv.filled[c.ep * c.T + c.tt];
+  float g;
+  if (p.td_ext) {  // VDN: the agent-coupled TD error was computed by vdn_td_kernel
+    g = p.td_ext[(size_t)c.b * c.T + c.tt];
+  } else {
+    const float rew = tv.rew[(c.ep * tv.N + c.agent) * c.T + c.tt];
+    const float done1 = (float)tv.done[c.ep * (c.T + 1) + c.tt + 1];
+    const float* tq = p.tq + (((size_t)c.agent * c.B + c.b) * (c.T + 1) + c.tt + 1) * c.A;
+    float tsel;
+    if (p.double_q) {  // dqn/model.py:138-143
+      int best = 0; float bv = qn[0];
+      for (int o = 1; o < c.A; ++o) if (qn[o] > bv) { bv = qn[o]; best = o; }
+      tsel = tq[best];
+    } else {
+      tsel = tq[0];
+      for (int o = 1; o < c.A; ++o) tsel = fmaxf(tsel, tq[o]);
+    }
+    const float y = rew + p.gamma * tsel * (1.f - done1);   // dqn/model.py:152
+    const float delta = q[act] - y;
+    st[0] += delta * delta * filled;                        // dqn/model.py:160-163
+    if (c.agent == 0) st[1] += filled;
+    g = 2.f * delta * filled;
+  }
+#pragma unroll
+  for (int o = 0; o < kOutPad; ++o) dq[o] = (o == act) ? g : 0.f;
+}
+
+__device__ __forceinline__ void head_a2c_critic(const TrainParams& p, const RowCtx& c, const float* q, float (&dq)[kOutPad], float (&st)[4]) {
+  const size_t i = ((size_t)c.agent * c.B + c.b) * c.T + c.tt;
+  const float filled = (float)p.src.traj.filled[c.ep * c.T + c.tt];
+  const float adv = p.returns[i] - q[0];                    // ac/model.py:214
+  p.adv_out[i] = adv;
+  st[3] += adv * adv * filled;                              // ac/model.py:221-222
+  if (c.agent == 0) st[1] += filled;
+  dq[0] = -2.f * adv * filled * p.value_coef;               // d(value_loss_coef * (R - V)^2)/dV
+}
+
+__device__ __forceinline__ void head_a2c_actor(const TrainParams& p, const RowCtx& c, const float* q, float (&dq)[kOutPad], float (&st)[4]) {
+  const TrajView& tv = p.src.traj;
+  const size_t i = ((size_t)c.agent * c.B + c.b) * c.T + c.tt;
+  const int act = tv.act[(c.ep * tv.N + c.agent) * c.T + c.tt];
+  const float filled = (float)tv.filled[c.ep * c.T + c.tt];
+  const float adv = p.adv[i];
+  float m = q[0];
+  for (int o = 1; o < c.A; ++o) m = fmaxf(m, q[o]);
+  float s = 0.f;
+  for (int o = 0; o < c.A; ++o) s += expf(q[o] - m);
+  const float lse = m + logf(s);
+  float ent = 0.f, pr[kOutPad], ls[kOutPad];
+#pragma unroll
+  for (int o = 0; o < kOutPad; ++o) {
+    ls[o] = o < c.A ? q[o] - lse : 0.f;                     // Categorical(logits) normalisation (ac/model.py:142-144)
+    pr[o] = o < c.A ? expf(ls[o]) : 0.f;
+    ent -= pr[o] * ls[o];
+  }
+  st[0] += -ls[act] * adv * filled;                         // ac/model.py:216-219
+  st[2] += ent * filled;
+#pragma unroll
+  for (int o = 0; o < kOutPad; ++o)
+    dq[o] = o < c.A ? filled * (adv * (pr[o] - (o == act ? 1.f : 0.f)) + p.entropy_coef * pr[o] * (ls[o] + ent)) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <int KP, int HEAD>
+__global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
   extern __shared__ __align__(16) float smem[];
   WeightSmem<KP> w(smem);
   float* X = smem + WeightSmem<KP>::kFloats;
   float* H1 = X + kTileRows * KP;
   float* H2 = H1 + kTileRows * kHidden;
-  float* Q = H2 + kTileRows * kHidden;  // q-values, then dq, then reduction scratch
-  float* carry = Q + kTileRows * kOutPad;  // q-values of the first row of the previously processed (higher) tile
+  float* Q = H2 + kTileRows * kHidden;  // network outputs, then dLoss/dOutput, then reduction scratch
+  float* carry = Q + kTileRows * kOutPad;  // outputs of the first row of the previously processed (higher) tile
   const ThreadCoord tc;
   const int t = threadIdx.x;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   float* gs = p.scratch + (size_t)blockIdx.x * p.scratch_pitch;
-  float loss_acc = 0.f, filled_acc = 0.f;
+  float st[4] = {0.f, 0.f, 0.f, 0.f};
   if (row_begin >= row_end) {  // idle CTA: its partial must still read as zero
     for (int i = t; i < p.lay.P; i += kMlpThreads) gs[i] = 0.f;
-    if (t == 0) { p.loss_part[2 * blockIdx.x] = 0.f; p.loss_part[2 * blockIdx.x + 1] = 0.f; }
+    if (t < 4) p.loss_part[4 * blockIdx.x + t] = 0.f;
     return;
   }
   w.load(p.theta + (size_t)net * p.lay.P, p.lay);
-  const int T = p.src.traj.T, A = p.lay.out, B = p.plan.units_per_agent;
+  RowCtx c; c.T = p.src.traj.T; c.A = p.lay.out; c.B = p.plan.units_per_agent;
   bool first = true;
-  // tiles from the top of the chunk downwards, so that q(t+1) of a tile's last row is already known
+  // tiles from the top of the chunk downwards, so that the next row's outputs of a tile's last row are already known
   for (int vr_hi = row_end; vr_hi > row_begin; vr_hi -= kTileRows) {
     const int vr0 = max(row_begin, vr_hi - kTileRows), nrows = vr_hi - vr0;
     __syncthreads();
@@ -219,7 +289,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dqn_train_kernel(DqnTrainParam
     __syncthreads();
     mlp_forward_tile<KP>(X, H1, H2, Q, w, tc);
     __syncthreads();
-    // ---- TD head: one thread per row -------------------------------------------------------------------------
     float dq[kOutPad];
 #pragma unroll
     for (int o = 0; o < kOutPad; ++o) dq[o] = 0.f;
@@ -229,38 +298,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dqn_train_kernel(DqnTrainParam
       for (int o = 0; o < kOutPad; ++o) q_first[o] = Q[o];
     }
     if (t < nrows) {
-      int agent, b, tt;
-      decode_row(p.plan, net, vr0 + t, agent, b, tt);
-      if (tt < T) {
-        const size_t ep = (size_t)p.src.idx[b];
-        const TrajView& tv = p.src.traj;
-        const int act = tv.act[(ep * tv.N + agent) * T + tt];
-        const float filled = (float)tv.filled[ep * T + tt];
-        float g;
-        if (p.td_ext) {  // VDN: the agent-coupled TD error was computed by vdn_td_kernel
-          g = p.td_ext[(size_t)b * T + tt];
-        } else {
-          const float rew = tv.rew[(ep * tv.N + agent) * T + tt];
-          const float done1 = (float)tv.done[ep * (T + 1) + tt + 1];
-          const float* qn = (t + 1 < nrows) ? (Q + (t + 1) * kOutPad) : carry;
-          const float* tq = p.tq + (((size_t)agent * B + b) * (T + 1) + tt + 1) * A;
-          float tsel;
-          if (p.double_q) {
-            int best = 0; float bv = qn[0];
-            for (int o = 1; o < A; ++o) if (qn[o] > bv) { bv = qn[o]; best = o; }
-            tsel = tq[best];
-          } else {
-            tsel = tq[0];
-            for (int o = 1; o < A; ++o) tsel = fmaxf(tsel, tq[o]);
-          }
-          const float y = rew + p.gamma * tsel * (1.f - done1);
-          const float delta = Q[t * kOutPad + act] - y;
-          loss_acc += delta * delta * filled;
-          if (agent == 0) filled_acc += filled;
-          g = 2.f * delta * filled;
-        }
-#pragma unroll
-        for (int o = 0; o < kOutPad; ++o) dq[o] = (o == act) ? g : 0.f;
+      decode_row(p.plan, net, vr0 + t, c.agent, c.b, c.tt);
+      if (c.tt < c.T) {
+        c.ep = (size_t)p.src.idx[c.b];
+        const float* q = Q + t * kOutPad;
+        if constexpr (HEAD == kHeadDqn) head_dqn(p, c, q, (t + 1 < nrows) ? q + kOutPad : carry, dq, st);
+        else if constexpr (HEAD == kHeadA2cCritic) head_a2c_critic(p, c, q, dq, st);
+        else head_a2c_actor(p, c, q, dq, st);
       }
     }
     __syncthreads();
@@ -276,16 +320,20 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dqn_train_kernel(DqnTrainParam
     mlp_backward_tile<KP>(X, H1, H2, Q, w, p.lay, gs, first, tc);
     first = false;
   }
-  // ---- per-CTA loss / filled sums (fixed-order tree: deterministic) ----------------------------------------------
+  // ---- per-CTA loss statistics (fixed-order tree: deterministic) ---------------------------------------------------
   __syncthreads();
   float* red = Q;
-  red[t] = loss_acc; red[kMlpThreads + t] = filled_acc;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red[k * kMlpThreads + t] = st[k];
   __syncthreads();
   for (int s = kMlpThreads / 2; s > 0; s >>= 1) {
-    if (t < s) { red[t] += red[t + s]; red[kMlpThreads + t] += red[kMlpThreads + t + s]; }
+    if (t < s) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red[k * kMlpThreads + t] += red[k * kMlpThreads + t + s];
+    }
     __syncthreads();
   }
-  if (t == 0) { p.loss_part[2 * blockIdx.x] = red[0]; p.loss_part[2 * blockIdx.x + 1] = red[kMlpThreads]; }
+  if (t < 4) p.loss_part[4 * blockIdx.x + t] = red[t * kMlpThreads];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -297,15 +345,16 @@ __global__ void grad_reduce_kernel(ReduceParams p) {
     float s = 0.f;
     for (int c = p.cta_begin[net]; c < p.cta_begin[net + 1]; ++c) s += p.scratch[(size_t)c * p.scratch_pitch + j];
     p.grad[i] = s;
-  } else if (i < n + 2) {
+  } else if (i < n + 4 && p.stats) {
     const int which = i - n;
-    float s = 0.f;
-    for (int c = 0; c < p.n_loss_parts; ++c) s += p.loss_part[2 * c + which];
-    p.grad[i] = s;
+    float s = p.stats_accumulate ? p.stats[which] : 0.f;
+    for (int c = 0; c < p.n_loss_parts; ++c) s += p.loss_part[4 * c + which];
+    p.stats[which] = s;
   }
 }
 
-// grad holds un-normalised sums followed by (loss_sum, filled_sum) -- possibly all-reduced over ranks.
+// grad holds un-normalised sums followed by 4 statistics (loss numerator, filled count, aux, aux) -- possibly
+// all-reduced over ranks.
 // Every CTA recomputes the global norm in the same order (bit-identical clip coefficient on every CTA and rank).
 __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
   __shared__ float red[256];
@@ -329,17 +378,25 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
     const float denom = sqrtf(v) / p.bc2_sqrt + p.eps;
     th = th - (p.lr / p.bc1) * (m / denom);
     p.m[i] = m; p.v[i] = v; p.theta[i] = th;
-    if (p.target_mode == 1) p.theta_tgt[i] = th;
-    else if (p.target_mode == 2) p.theta_tgt[i] = (1.f - p.tau) * p.theta_tgt[i] + p.tau * th;
+    const int j = i - p.tgt_begin;
+    if (j >= 0 && j < p.tgt_n) {
+      if (p.target_mode == 1) p.theta_tgt[j] = th;
+      else if (p.target_mode == 2) p.theta_tgt[j] = (1.f - p.tau) * p.theta_tgt[j] + p.tau * th;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && p.loss_out) { p.loss_out[0] = p.grad[p.n] * inv_fill; p.loss_out[1] = norm; }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.loss_out) {
+    p.loss_out[0] = p.grad[p.n] * inv_fill; p.loss_out[1] = norm; p.loss_out[2] = p.grad[p.n + 2] * inv_fill;
+    p.loss_out[3] = p.grad[p.n + 3] * inv_fill; p.loss_out[4] = p.grad[p.n + 1]; p.loss_out[5] = 0.f;
+  }
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------
 int learner_kernels_init(int in_dim) {
   MARL_REQUIRE(in_dim >= 1 && in_dim <= 16, "learner kernels: observation width %d not supported yet (1..16)", in_dim);
   MARL_CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)forward_smem_bytes<16>()));
-  MARL_CUDA_TRY(cudaFuncSetAttribute(dqn_train_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<16, kHeadDqn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<16, kHeadA2cCritic>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<16, kHeadA2cActor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
   return MARL_OK;
 }
 
@@ -349,14 +406,19 @@ int launch_mlp_forward(const FwdParams& p, cudaStream_t st) {
   return MARL_OK;
 }
 
-int launch_dqn_train(const DqnTrainParams& p, cudaStream_t st) {
-  dqn_train_kernel<16><<<p.plan.cta_begin[p.plan.n_nets], kMlpThreads, train_smem_bytes<16>(), st>>>(p);
+int launch_train(const TrainParams& p, int head, cudaStream_t st) {
+  const int grid = p.plan.cta_begin[p.plan.n_nets];
+  const size_t sm = train_smem_bytes<16>();
+  if (head == kHeadDqn) train_kernel<16, kHeadDqn><<<grid, kMlpThreads, sm, st>>>(p);
+  else if (head == kHeadA2cCritic) train_kernel<16, kHeadA2cCritic><<<grid, kMlpThreads, sm, st>>>(p);
+  else if (head == kHeadA2cActor) train_kernel<16, kHeadA2cActor><<<grid, kMlpThreads, sm, st>>>(p);
+  else { set_error("launch_train: unknown head %d", head); return MARL_EINVAL; }
   MARL_CUDA_TRY(cudaGetLastError());
   return MARL_OK;
 }
 
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
-  const int n = p.n_nets * p.P + 2;
+  const int n = p.n_nets * p.P + 4;
   grad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p);
   MARL_CUDA_TRY(cudaGetLastError());
   return MARL_OK;

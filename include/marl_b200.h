@@ -166,8 +166,8 @@ typedef struct marl_dqn marl_dqn;
 int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_batch, int32_t max_T, int32_t device,
                     marl_dqn** out);
 int marl_dqn_destroy(marl_dqn* q);
-/* Device pointers to the flat parameter / optimiser state ([n_nets*P] floats each; grad has 2 extra floats:
- * loss numerator and filled count).  Initialise theta through these (orthogonal init is done by the caller). */
+/* Device pointers to the flat parameter / optimiser state ([n_nets*P] floats each; grad has 4 extra floats:
+ * loss numerator, filled count, 2 spare).  Initialise theta through these (orthogonal init is done by the caller). */
 int marl_dqn_param_ptrs(marl_dqn* q, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad,
                         int64_t* n_params);
 int marl_dqn_sync_target(marl_dqn* q, void* stream);        /* hard_update (dqn/model.py:195-196) */
@@ -178,9 +178,9 @@ int marl_replay_sample(uint64_t seed, uint64_t update_idx, int32_t batch, int32_
                        void* stream);
 /* QNetwork.update (dqn/model.py:165-174) split at the point where data-parallel ranks exchange:
  *   _grads: rb.sample gather + _compute_loss + backward  -> un-normalised gradient sums in `grad`
- *   (caller may all-reduce grad[0 .. n_params+2) over ranks here)
- *   _apply: / filled.sum(), clip_grad_norm_, Adam.step, updates += 1, update_target; loss_out device float[2]
- *           = (loss, gradient norm before clipping) or NULL */
+ *   (caller may all-reduce grad[0 .. n_params+4) over ranks here)
+ *   _apply: / filled.sum(), clip_grad_norm_, Adam.step, updates += 1, update_target; loss_out device float[6]
+ *           = (loss, gradient norm before clipping, 0, 0, filled count, 0) or NULL */
 int marl_dqn_update_grads(marl_dqn* q, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch,
                           void* stream);
 int marl_dqn_update_apply(marl_dqn* q, float* loss_out, void* stream);
@@ -193,6 +193,47 @@ int marl_dqn_counters(marl_dqn* q, int64_t* updates, int64_t* last_target_update
 /* measurement hook (bench.py roofline leg): CUDA-event time of the training-kernel launches between enable=1 and enable=0 */
 int marl_dqn_timing(marl_dqn* q, int32_t enable, float* total_ms, int32_t* count);
 int marl_dqn_set_counters(marl_dqn* q, int64_t updates, int64_t last_target_update);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Independent actor-critic learner (IA2C).  Replaces marlbase/ac/model.py A2CNetwork (22-246) with a
+ * decentralised critic (ia2c.yaml:18), independent or shared per-agent networks.
+ * theta = [actor nets | critic nets] flat, theta_tgt = target critic; per-net order as for marl_dqn.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float   lr;                             /* ia2c.yaml:29 */
+  float   gamma;                          /* ia2c.yaml:34 */
+  float   grad_clip;                      /* ia2c.yaml:31 (False -> 0) */
+  int32_t n_steps;                        /* ia2c.yaml:33 */
+  float   entropy_coef;                   /* ia2c.yaml:35 */
+  float   value_loss_coef;                /* ia2c.yaml:36 */
+  float   target_update_interval_or_tau;  /* ia2c.yaml:40; compared against the ENVIRONMENT step (ac/model.py:233-237) */
+  float   beta1, beta2, eps;              /* Adam defaults */
+} marl_a2c_hp;
+
+typedef struct marl_a2c marl_a2c;
+
+int marl_a2c_create(const marl_mlp_cfg* actor, const marl_mlp_cfg* critic, const marl_a2c_hp* hp, int32_t max_envs,
+                    int32_t max_T, int32_t device, marl_a2c** out);
+int marl_a2c_destroy(marl_a2c* a);
+int marl_a2c_param_ptrs(marl_a2c* a, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad,
+                        int64_t* n_actor, int64_t* n_critic);
+/* device scratch of the last update (parity tests): target values [N][P][T+1], n-step returns [N][P][T], advantages [N][P][T] */
+int marl_a2c_scratch_ptrs(marl_a2c* a, float** target_values, float** returns, float** advantages);
+int marl_a2c_sync_target(marl_a2c* a, void* stream);      /* soft_update(1.0) (ac/model.py:101,184-187) */
+/* actor pass of A2CNetwork.act (ac/model.py:148-150): obs float[E][N][in] -> logits float[E][N][n_actions]; sampling
+ * happens in marl_lbf_rollout_step(policy = 2) */
+int marl_a2c_forward_actor(marl_a2c* a, const float* obs, int32_t n_envs, float* logits_out, void* stream);
+int marl_a2c_forward_critic(marl_a2c* a, const float* obs, int32_t n_envs, int32_t use_target, float* values_out,
+                            void* stream);
+/* A2CNetwork.update (ac/model.py:189-246) on the on-policy batch held in a trajectory store of capacity >= n_envs
+ * (slot e = env e), split where data-parallel ranks exchange grad[0 .. n_actor+n_critic+4):
+ *   _grads: target-critic pass, n-step returns, critic + actor forward/loss/backward -> gradient sums + statistics
+ *   _apply: / filled.sum(), optional clip, Adam over actor+critic, target sync when step % interval == 0;
+ *           metrics_out device float[6] = (policy-gradient term, gradient norm, entropy, value_loss, filled count, 0) */
+int marl_a2c_update_grads(marl_a2c* a, const marl_traj_view* batch, int32_t n_envs, void* stream);
+int marl_a2c_update_apply(marl_a2c* a, int64_t step, float* metrics_out, void* stream);
+int marl_a2c_update(marl_a2c* a, const marl_traj_view* batch, int32_t n_envs, int64_t step, float* metrics_out,
+                    void* stream);
 
 #ifdef __cplusplus
 }
