@@ -52,18 +52,51 @@ __device__ __forceinline__ const float* row_ptr(const RowSource& s, int agent, i
   return s.traj.obs + ((ep * s.traj.N + agent) * (size_t)(s.traj.T + 1) + off) * s.traj.D;
 }
 
-// Fill the [128][KP] input tile with rows [vr0, vr0 + nrows) of `net`, zero padded in both directions.
+// Per-tile row metadata staged in shared memory by the first 128 threads (one row each): the source pointer of the
+// row's observation and, for training passes, the scalars the loss head needs.  Two dependent global latencies per tile
+// (episode index, then its fields) instead of a dependent chain per element / per head.
+struct RowMeta {
+  const float* src[kTileRows];
+  int act[kTileRows];
+  float rew[kTileRows];
+  int flags[kTileRows];  // bit 0: filled[t], bit 1: done[t+1]
+  static constexpr int kBytes = kTileRows * (8 + 4 + 4 + 4);
+};
+
+template <bool kWithScalars>
+__device__ __forceinline__ void setup_rows(RowMeta* m, const RowPlan& p, const RowSource& s, int net, int vr0, int nrows) {
+  const int r = threadIdx.x;
+  if (r >= kTileRows) return;
+  const float* src = nullptr; int act = 0, flags = 0; float rew = 0.f;
+  if (r < nrows) {
+    int agent, unit, off;
+    decode_row(p, net, vr0 + r, agent, unit, off);
+    if (s.mode == 0) {
+      src = s.dense + ((size_t)unit * s.N + agent) * s.D;
+    } else {
+      const size_t ep = (size_t)s.idx[unit];
+      const TrajView& tv = s.traj;
+      src = tv.obs + ((ep * tv.N + agent) * (size_t)(tv.T + 1) + off) * tv.D;
+      if (kWithScalars && off < tv.T) {
+        act = tv.act[(ep * tv.N + agent) * tv.T + off];
+        rew = tv.rew[(ep * tv.N + agent) * tv.T + off];
+        flags = (int)tv.filled[ep * tv.T + off] | ((int)tv.done[ep * (tv.T + 1) + off + 1] << 1);
+      }
+    }
+  }
+  m->src[r] = src; m->act[r] = act; m->rew[r] = rew; m->flags[r] = flags;
+}
+
+// Fill the [128][KP] input tile from the staged row pointers (asynchronous copies; zero padding in both directions).
+// Caller: cp_async_wait_all() + __syncthreads() before the tile is read.
 template <int KP>
-__device__ __forceinline__ void gather_tile(float* X, const RowPlan& p, const RowSource& s, int net, int vr0, int nrows) {
+__device__ __forceinline__ void gather_tile_async(float* X, const RowMeta* m, int D) {
+#pragma unroll 4
   for (int i = threadIdx.x; i < kTileRows * KP; i += kMlpThreads) {
     const int r = i / KP, k = i - r * KP;
-    float v = 0.f;
-    if (r < nrows && k < s.D) {
-      int agent, unit, off;
-      decode_row(p, net, vr0 + r, agent, unit, off);
-      v = row_ptr(s, agent, unit, off)[k];
-    }
-    at1<KP>(X, r, k) = v;
+    const float* src = m->src[r];
+    if (src != nullptr && k < D) cp_async4(&at1<KP>(X, r, k), src + k);
+    else at1<KP>(X, r, k) = 0.f;
   }
 }
 
@@ -123,9 +156,9 @@ int launch_grad_reduce(const ReduceParams& p, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
 template <int KP>
-constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + kTileRows * KP + 2 * kTileRows * kHidden + kTileRows * kOutPad); }
+constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + kTileRows * KP + 2 * kTileRows * kHidden + kTileRows * kOutPad + 16) + RowMeta::kBytes; }
 template <int KP>
-constexpr size_t train_smem_bytes() { return forward_smem_bytes<KP>() + sizeof(float) * 16; }
+constexpr size_t train_smem_bytes() { return forward_smem_bytes<KP>(); }
 
 // ---- host-side planning -----------------------------------------------------------------------------------------
 struct NetSet {

@@ -24,15 +24,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(FwdParams p
   float* H1 = X + kTileRows * KP;
   float* H2 = H1 + kTileRows * kHidden;
   float* Q = H2 + kTileRows * kHidden;
+  RowMeta* meta = reinterpret_cast<RowMeta*>(Q + kTileRows * kOutPad + 16);
   const ThreadCoord tc;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   if (row_begin >= row_end) return;
-  w.load(p.theta + (size_t)net * p.lay.P, p.lay);
+  w.load_async(p.theta + (size_t)net * p.lay.P, p.lay);
   for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
     const int nrows = min(kTileRows, row_end - vr0);
     __syncthreads();
-    gather_tile<KP>(X, p.plan, p.src, net, vr0, nrows);
+    setup_rows<false>(meta, p.plan, p.src, net, vr0, nrows);
+    __syncthreads();
+    gather_tile_async<KP>(X, meta, p.src.D);
+    cp_async_wait_all();
     __syncthreads();
     mlp_forward_tile<KP>(X, H1, H2, Q, w, tc);
     __syncthreads();
@@ -49,11 +53,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(FwdParams p
 
 // ------------------------------------------------------------------------------------------------------------
 // per-CTA gradient partial: first tile stores, later tiles accumulate (plain loads/stores: the region is private)
-__device__ __forceinline__ void rmw(float* dst, float v, bool first) { *dst = first ? v : (*dst + v); }
+// (the accumulation is a RED: no value returns to the SM, so nothing waits on the L2 round trip; one thread per address
+// and tiles in program order keep the sum order fixed)
+__device__ __forceinline__ void rmw(float* dst, float v, bool first) {
+  if (first) *dst = v; else atomicAdd(dst, v);
+}
 __device__ __forceinline__ void rmw4(float* dst, float4 v, bool first) {
-  float4* d = reinterpret_cast<float4*>(dst);
-  if (!first) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-  *d = v;
+  if (first) *reinterpret_cast<float4*>(dst) = v; else atomicAdd(reinterpret_cast<float4*>(dst), v);
 }
 
 // Backward of one tile.  On entry: X, H1, H2 hold the forward activations, DQ[128][8] holds dLoss/dq (zero rows
@@ -190,18 +196,16 @@ __device__ __forceinline__ void mlp_backward_tile(const float* X, float* H1, flo
 // ------------------------------------------------------------------------------------------------------------
 // Loss heads: one thread per row of the tile.  `q` = this row's network outputs, `qn` = next row's (same episode),
 // results: dq[0..7] = dLoss/d(output) un-normalised, st[0..3] += loss statistics.
-struct RowCtx { int agent, b, tt, T, A, B; size_t ep; };
+struct RowCtx { int agent, b, tt, T, A, B; int act; float rew, filled, done1; };
 
 __device__ __forceinline__ void head_dqn(const TrainParams& p, const RowCtx& c, const float* q, const float* qn, float (&dq)[kOutPad], float (&st)[4]) {
-  const TrajView& tv = p.src.traj;
-  const int act = tv.act[(c.ep * tv.N + c.agent) * c.T + c.tt];
-  const float filled = (float)tv.filled[c.ep * c.T + c.tt];
+  const int act = c.act;
+  const float filled = c.filled;
   float g;
   if (p.td_ext) {  // VDN: the agent-coupled TD error was computed by vdn_td_kernel
     g = p.td_ext[(size_t)c.b * c.T + c.tt];
   } else {
-    const float rew = tv.rew[(c.ep * tv.N + c.agent) * c.T + c.tt];
-    const float done1 = (float)tv.done[c.ep * (c.T + 1) + c.tt + 1];
+    const float rew = c.rew, done1 = c.done1;
     const float* tq = p.tq + (((size_t)c.agent * c.B + c.b) * (c.T + 1) + c.tt + 1) * c.A;
     float tsel;
     if (p.double_q) {  // dqn/model.py:138-143
@@ -224,7 +228,7 @@ __device__ __forceinline__ void head_dqn(const TrainParams& p, const RowCtx& c, 
 
 __device__ __forceinline__ void head_a2c_critic(const TrainParams& p, const RowCtx& c, const float* q, float (&dq)[kOutPad], float (&st)[4]) {
   const size_t i = ((size_t)c.agent * c.B + c.b) * c.T + c.tt;
-  const float filled = (float)p.src.traj.filled[c.ep * c.T + c.tt];
+  const float filled = c.filled;
   const float adv = p.returns[i] - q[0];                    // ac/model.py:214
   p.adv_out[i] = adv;
   st[3] += adv * adv * filled;                              // ac/model.py:221-222
@@ -233,10 +237,9 @@ __device__ __forceinline__ void head_a2c_critic(const TrainParams& p, const RowC
 }
 
 __device__ __forceinline__ void head_a2c_actor(const TrainParams& p, const RowCtx& c, const float* q, float (&dq)[kOutPad], float (&st)[4]) {
-  const TrajView& tv = p.src.traj;
   const size_t i = ((size_t)c.agent * c.B + c.b) * c.T + c.tt;
-  const int act = tv.act[(c.ep * tv.N + c.agent) * c.T + c.tt];
-  const float filled = (float)tv.filled[c.ep * c.T + c.tt];
+  const int act = c.act;
+  const float filled = c.filled;
   const float adv = p.adv[i];
   float m = q[0];
   for (int o = 1; o < c.A; ++o) m = fmaxf(m, q[o]);
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
   float* H2 = H1 + kTileRows * kHidden;
   float* Q = H2 + kTileRows * kHidden;  // network outputs, then dLoss/dOutput, then reduction scratch
   float* carry = Q + kTileRows * kOutPad;  // outputs of the first row of the previously processed (higher) tile
+  RowMeta* meta = reinterpret_cast<RowMeta*>(carry + 16);
   const ThreadCoord tc;
   const int t = threadIdx.x;
   int net, row_begin, row_end;
@@ -278,14 +282,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
     if (t < 4) p.loss_part[4 * blockIdx.x + t] = 0.f;
     return;
   }
-  w.load(p.theta + (size_t)net * p.lay.P, p.lay);
+  w.load_async(p.theta + (size_t)net * p.lay.P, p.lay);
   RowCtx c; c.T = p.src.traj.T; c.A = p.lay.out; c.B = p.plan.units_per_agent;
   bool first = true;
   // tiles from the top of the chunk downwards, so that the next row's outputs of a tile's last row are already known
   for (int vr_hi = row_end; vr_hi > row_begin; vr_hi -= kTileRows) {
     const int vr0 = max(row_begin, vr_hi - kTileRows), nrows = vr_hi - vr0;
     __syncthreads();
-    gather_tile<KP>(X, p.plan, p.src, net, vr0, nrows);
+    setup_rows<true>(meta, p.plan, p.src, net, vr0, nrows);
+    __syncthreads();
+    gather_tile_async<KP>(X, meta, p.src.D);
+    cp_async_wait_all();
     __syncthreads();
     mlp_forward_tile<KP>(X, H1, H2, Q, w, tc);
     __syncthreads();
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
     if (t < nrows) {
       decode_row(p.plan, net, vr0 + t, c.agent, c.b, c.tt);
       if (c.tt < c.T) {
-        c.ep = (size_t)p.src.idx[c.b];
+        c.act = meta->act[t]; c.rew = meta->rew[t]; c.filled = (float)(meta->flags[t] & 1); c.done1 = (float)((meta->flags[t] >> 1) & 1);
         const float* q = Q + t * kOutPad;
         if constexpr (HEAD == kHeadDqn) head_dqn(p, c, q, (t + 1 < nrows) ? q + kOutPad : carry, dq, st);
         else if constexpr (HEAD == kHeadA2cCritic) head_a2c_critic(p, c, q, dq, st);
@@ -342,9 +349,18 @@ __global__ void grad_reduce_kernel(ReduceParams p) {
   const int n = p.n_nets * p.P;
   if (i < n) {
     const int net = i / p.P, j = i - net * p.P;
-    float s = 0.f;
-    for (int c = p.cta_begin[net]; c < p.cta_begin[net + 1]; ++c) s += p.scratch[(size_t)c * p.scratch_pitch + j];
-    p.grad[i] = s;
+    // fixed association (four interleaved chains, then a fixed combine): deterministic, and the loads overlap
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int c0 = p.cta_begin[net], c1 = p.cta_begin[net + 1];
+    const float* base = p.scratch + j;
+    int c = c0;
+#pragma unroll 2
+    for (; c + 3 < c1; c += 4) {
+      s0 += base[(size_t)c * p.scratch_pitch]; s1 += base[(size_t)(c + 1) * p.scratch_pitch];
+      s2 += base[(size_t)(c + 2) * p.scratch_pitch]; s3 += base[(size_t)(c + 3) * p.scratch_pitch];
+    }
+    for (; c < c1; ++c) s0 += base[(size_t)c * p.scratch_pitch];
+    p.grad[i] = (s0 + s1) + (s2 + s3);
   } else if (i < n + 4 && p.stats) {
     const int which = i - n;
     float s = p.stats_accumulate ? p.stats[which] : 0.f;
@@ -362,7 +378,15 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
   float clip = 1.f, norm = 0.f;
   {
     float s = 0.f;
-    for (int i = threadIdx.x; i < p.n; i += 256) { const float g = p.grad[i] * inv_fill; s = fmaf(g, g, s); }
+    const int n4 = p.n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(p.grad);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 g = g4[i];
+      const float a = g.x * inv_fill, b = g.y * inv_fill, c = g.z * inv_fill, d = g.w * inv_fill;
+      s = fmaf(a, a, s); s = fmaf(b, b, s); s = fmaf(c, c, s); s = fmaf(d, d, s);
+    }
+    for (int i = 4 * n4 + threadIdx.x; i < p.n; i += 256) { const float g = p.grad[i] * inv_fill; s = fmaf(g, g, s); }
     red[threadIdx.x] = s;
     __syncthreads();
     for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }

@@ -53,6 +53,13 @@ __device__ __forceinline__ const float& at1(const float* base, int row, int k) {
   return base[row * KP + swz<KP>(row, k >> 2) * 4 + (k & 3)];
 }
 
+// 4-byte asynchronous global->shared copy (LDGSTS): fire and forget, completion via cp_async_wait_all + barrier
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void zero_acc(float (&acc)[8][8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -178,19 +185,21 @@ struct WeightSmem {
   __device__ explicit WeightSmem(float* base) {
     w1 = base; w2 = w1 + kHidden * KP; w3 = w2 + kHidden * kHidden; b1 = w3 + kOutPad * kHidden; b2 = b1 + kHidden; b3 = b2 + kHidden;
   }
-  // cooperative load from global params (native layouts) into the swizzled smem layouts
-  __device__ void load(const float* __restrict__ theta, const NetLayout& l) {
+  // cooperative asynchronous load from global params (native layouts) into the swizzled smem layouts; 4-byte
+  // cp.async because theta + net*P is only 4-byte aligned.  Caller: cp_async_wait_all() + __syncthreads() before use.
+  __device__ void load_async(const float* __restrict__ theta, const NetLayout& l) {
     for (int i = threadIdx.x; i < kHidden * KP; i += kMlpThreads) {
       const int n = i / KP, k = i % KP;
-      at1<KP>(w1, n, k) = k < l.in ? theta[l.w1 + n * l.in + k] : 0.f;
+      if (k < l.in) cp_async4(&at1<KP>(w1, n, k), theta + l.w1 + n * l.in + k);
+      else at1<KP>(w1, n, k) = 0.f;
     }
-    for (int i = threadIdx.x; i < kHidden * kHidden; i += kMlpThreads)  // scalar: theta + net*P is only 4-byte aligned
-      at1<kHidden>(w2, i / kHidden, i % kHidden) = theta[l.w2 + i];
+#pragma unroll 8
+    for (int i = threadIdx.x; i < kHidden * kHidden; i += kMlpThreads) cp_async4(&at1<kHidden>(w2, i / kHidden, i % kHidden), theta + l.w2 + i);
     for (int i = threadIdx.x; i < kOutPad * kHidden; i += kMlpThreads) {
-      const int o = i / kHidden;
-      w3[i] = o < l.out ? theta[l.w3 + i] : 0.f;
+      if (i / kHidden < l.out) cp_async4(w3 + i, theta + l.w3 + i);
+      else w3[i] = 0.f;
     }
-    for (int i = threadIdx.x; i < kHidden; i += kMlpThreads) { b1[i] = theta[l.b1 + i]; b2[i] = theta[l.b2 + i]; }
+    for (int i = threadIdx.x; i < kHidden; i += kMlpThreads) { cp_async4(b1 + i, theta + l.b1 + i); cp_async4(b2 + i, theta + l.b2 + i); }
     if (threadIdx.x < kOutPad) b3[threadIdx.x] = threadIdx.x < l.out ? theta[l.b3 + threadIdx.x] : 0.f;
   }
 };
