@@ -156,7 +156,7 @@ int launch_grad_reduce(const ReduceParams& p, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
 template <int KP>
-constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + kTileRows * KP + 2 * kTileRows * kHidden + kTileRows * kOutPad + 16) + RowMeta::kBytes; }
+constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + kTileRows * pitch_of<KP>() + 2 * kTileRows * kPitchH + kTileRows * kOutPad + 16) + RowMeta::kBytes; }
 template <int KP>
 constexpr size_t train_smem_bytes() { return forward_smem_bytes<KP>(); }
 

@@ -21,9 +21,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(FwdParams p
   extern __shared__ __align__(16) float smem[];
   WeightSmem<KP> w(smem);
   float* X = smem + WeightSmem<KP>::kFloats;
-  float* H1 = X + kTileRows * KP;
-  float* H2 = H1 + kTileRows * kHidden;
-  float* Q = H2 + kTileRows * kHidden;
+  float* H1 = X + kTileRows * pitch_of<KP>();
+  float* H2 = H1 + kTileRows * kPitchH;
+  float* Q = H2 + kTileRows * kPitchH;
   RowMeta* meta = reinterpret_cast<RowMeta*>(Q + kTileRows * kOutPad + 16);
   const ThreadCoord tc;
   int net, row_begin, row_end;
@@ -266,9 +266,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
   extern __shared__ __align__(16) float smem[];
   WeightSmem<KP> w(smem);
   float* X = smem + WeightSmem<KP>::kFloats;
-  float* H1 = X + kTileRows * KP;
-  float* H2 = H1 + kTileRows * kHidden;
-  float* Q = H2 + kTileRows * kHidden;  // network outputs, then dLoss/dOutput, then reduction scratch
+  float* H1 = X + kTileRows * pitch_of<KP>();
+  float* H2 = H1 + kTileRows * kPitchH;
+  float* Q = H2 + kTileRows * kPitchH;  // network outputs, then dLoss/dOutput, then reduction scratch
   float* carry = Q + kTileRows * kOutPad;  // outputs of the first row of the previously processed (higher) tile
   RowMeta* meta = reinterpret_cast<RowMeta*>(carry + 16);
   const ThreadCoord tc;

@@ -5,9 +5,9 @@
 // (MultiAgentIndependentNetwork), :176-300 (MultiAgentSharedNetwork).
 //
 // Tile shape: R = 128 rows (one row = one observation of one agent) x H = 128 features, 256 threads, every
-// thread owns an 8x8 register block.  All activations and weights are row-major [row][K] in shared memory with the
-// K pitch equal to the padded width (no padding bytes) and the 16-byte chunk index XOR-swizzled with the row, so
-// that every 128-bit shared load of the three GEMM forms below is bank-conflict free:
+// thread owns an 8x8 register block.  All activations and weights are row-major [row][K] in shared memory; 128-wide
+// tiles use a 132-float pitch, 16-wide tiles an XOR swizzle, so that every 128-bit shared load of the three GEMM forms
+// below is bank-conflict free:
 //   NT  C[r][n] = sum_k A[r][k] * B[n][k]     (forward layers: A = activations, B = nn.Linear weight [out][in])
 //   TN  C[m][n] = sum_r A[r][m] * B[r][n]     (weight gradients: A = dOut, B = layer input)
 //   NN  C[r][n] = sum_k A[r][k] * B[k][n]     (input gradients: B = nn.Linear weight in its native layout)
@@ -30,27 +30,36 @@ struct ThreadCoord {
   }
 };
 
-// physical 16-byte chunk of logical chunk c in `row` for a pitch of KP floats
+// Row pitch (floats) of a [rows][KP] shared-memory tile.  128-wide tiles are padded to 132 floats: linear addresses
+// (base register + immediate offsets in the unrolled GEMM loops, no per-load address arithmetic) and still conflict
+// free for every 128-bit access pattern below (row stride 132 words = 4 banks).  Narrow tiles (K = 16: observations,
+// first-layer weights) keep a dense pitch with the 16-byte chunk index XOR-swizzled by the row.
+template <int KP>
+constexpr int pitch_of() { return KP == 128 ? 132 : KP; }
+constexpr int kPitchH = 132;
+
+// physical 16-byte chunk of logical chunk c in `row`
 template <int KP>
 __device__ __forceinline__ int swz(int row, int c) {
-  if constexpr (KP >= 32) return c ^ (row & 7);
+  if constexpr (KP == 128) return c;
+  else if constexpr (KP >= 32) return c ^ (row & 7);
   else return c ^ ((row >> 1) & 3);
 }
 template <int KP>
 __device__ __forceinline__ float4& at4(float* base, int row, int c) {
-  return reinterpret_cast<float4*>(base + row * KP)[swz<KP>(row, c)];
+  return reinterpret_cast<float4*>(base + row * pitch_of<KP>())[swz<KP>(row, c)];
 }
 template <int KP>
 __device__ __forceinline__ const float4& at4(const float* base, int row, int c) {
-  return reinterpret_cast<const float4*>(base + row * KP)[swz<KP>(row, c)];
+  return reinterpret_cast<const float4*>(base + row * pitch_of<KP>())[swz<KP>(row, c)];
 }
 template <int KP>
 __device__ __forceinline__ float& at1(float* base, int row, int k) {
-  return base[row * KP + swz<KP>(row, k >> 2) * 4 + (k & 3)];
+  return base[row * pitch_of<KP>() + swz<KP>(row, k >> 2) * 4 + (k & 3)];
 }
 template <int KP>
 __device__ __forceinline__ const float& at1(const float* base, int row, int k) {
-  return base[row * KP + swz<KP>(row, k >> 2) * 4 + (k & 3)];
+  return base[row * pitch_of<KP>() + swz<KP>(row, k >> 2) * 4 + (k & 3)];
 }
 
 // 4-byte asynchronous global->shared copy (LDGSTS): fire and forget, completion via cp_async_wait_all + barrier
@@ -180,10 +189,10 @@ struct NetLayout {
 // Shared-memory weight block of one network.
 template <int KP>
 struct WeightSmem {
-  static constexpr int kFloats = kHidden * KP + kHidden * kHidden + kOutPad * kHidden + kHidden + kHidden + kOutPad;
+  static constexpr int kFloats = kHidden * pitch_of<KP>() + kHidden * kPitchH + kOutPad * kHidden + kHidden + kHidden + kOutPad;
   float* w1; float* w2; float* w3; float* b1; float* b2; float* b3;
   __device__ explicit WeightSmem(float* base) {
-    w1 = base; w2 = w1 + kHidden * KP; w3 = w2 + kHidden * kHidden; b1 = w3 + kOutPad * kHidden; b2 = b1 + kHidden; b3 = b2 + kHidden;
+    w1 = base; w2 = w1 + kHidden * pitch_of<KP>(); w3 = w2 + kHidden * kPitchH; b1 = w3 + kOutPad * kHidden; b2 = b1 + kHidden; b3 = b2 + kHidden;
   }
   // cooperative asynchronous load from global params (native layouts) into the swizzled smem layouts; 4-byte
   // cp.async because theta + net*P is only 4-byte aligned.  Caller: cp_async_wait_all() + __syncthreads() before use.
