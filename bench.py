@@ -98,11 +98,12 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     # each "step": every core runs `eps` iterations of (collect one 25-step episode with one env; one update at batch_size)
-    eps = 2
+    eps = 3
     rounds = cpu_loop.run_parallel(LBF_KW, args.batch, cores, prefill=args.batch, n_episodes=eps, n_rounds=args.warmup + args.steps)
     timed = rounds[args.warmup:]
-    steps, secs = sum(r[0] for r in timed), sum(r[1] for r in timed)
-    value = steps / secs
+    # independent copies: whole-machine throughput = sum of the copies' own rates (a straggler does not stall the others)
+    value = sum(r[2] for r in timed) / len(timed)
+    secs = sum(r[1] for r in timed)
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -113,7 +114,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -276,7 +277,7 @@ def run_b200(args):
             "roofline": roofline, "updates_per_sec": U * args.steps * world / (ms / 1e3), "env_steps_timed": n_steps}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -296,8 +297,18 @@ def cpu_baseline(args):
                       f"pure-Python LBF restatement + PyTorch-CPU learner, {secs:.1f} s"}
 
 
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library prints) was redirected to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stray prints of other libraries must not pollute the JSON contract
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -6,6 +6,8 @@
 
 namespace marl {
 
+constexpr int kMaxObsDim = 32;  // KP = 16 or 32 float input tiles
+
 struct TrajView {  // device view of marl_traj_view
   const float* obs; const int32_t* act; const float* rew; const uint8_t* done; const uint8_t* filled;
   int capacity, N, T, D;
@@ -156,7 +158,7 @@ int launch_grad_reduce(const ReduceParams& p, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
 template <int KP>
-constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + kTileRows * pitch_of<KP>() + 2 * kTileRows * kPitchH + kTileRows * kOutPad + 16) + RowMeta::kBytes; }
+constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + 2 * kTileRows * kPitchH + kTileRows * kOutPad + 16) + RowMeta::kBytes; }
 template <int KP>
 constexpr size_t train_smem_bytes() { return forward_smem_bytes<KP>(); }
 
@@ -216,7 +218,7 @@ inline int check_mlp_cfg(const marl_mlp_cfg* cfg, const char* who) {
   MARL_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= MARL_MAX_AGENTS, "%s: n_agents out of range", who);
   MARL_REQUIRE(cfg->n_nets >= 1 && cfg->n_nets <= cfg->n_agents, "%s: n_nets out of range", who);
   MARL_REQUIRE(cfg->hidden == kHidden, "%s: only layers=[128,128] is implemented on the B200 path (got hidden=%d)", who, cfg->hidden);
-  MARL_REQUIRE(cfg->in_dim >= 1 && cfg->in_dim <= 16, "%s: obs dim %d not supported yet (1..16)", who, cfg->in_dim);
+  MARL_REQUIRE(cfg->in_dim >= 1 && cfg->in_dim <= kMaxObsDim, "%s: obs dim %d not supported (1..%d)", who, cfg->in_dim, kMaxObsDim);
   MARL_REQUIRE(cfg->out_dim >= 1 && cfg->out_dim <= kOutPad, "%s: output width %d not supported (1..%d)", who, cfg->out_dim, kOutPad);
   for (int a = 0; a < cfg->n_agents; ++a) MARL_REQUIRE(cfg->agent_net[a] >= 0 && cfg->agent_net[a] < cfg->n_nets, "%s: agent_net[%d] out of range", who, a);
   return MARL_OK;

@@ -20,9 +20,9 @@ template <int KP>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(FwdParams p) {
   extern __shared__ __align__(16) float smem[];
   WeightSmem<KP> w(smem);
-  float* X = smem + WeightSmem<KP>::kFloats;
-  float* H1 = X + kTileRows * pitch_of<KP>();
+  float* H1 = smem + WeightSmem<KP>::kFloats;
   float* H2 = H1 + kTileRows * kPitchH;
+  float* X = H2;  // the input tile lives in the H2 region until layer 2 overwrites it
   float* Q = H2 + kTileRows * kPitchH;
   RowMeta* meta = reinterpret_cast<RowMeta*>(Q + kTileRows * kOutPad + 16);
   const ThreadCoord tc;
@@ -65,8 +65,8 @@ __device__ __forceinline__ void rmw4(float* dst, float4 v, bool first) {
 // Backward of one tile.  On entry: X, H1, H2 hold the forward activations, DQ[128][8] holds dLoss/dq (zero rows
 // beyond the valid ones).  gs = this CTA's gradient partial [P].  Uses DQ as scratch after it is consumed.
 template <int KP>
-__device__ __forceinline__ void mlp_backward_tile(const float* X, float* H1, float* H2, float* DQ, const WeightSmem<KP>& w, const NetLayout& lay,
-                                                  float* gs, bool first, const ThreadCoord& tc) {
+__device__ __forceinline__ void mlp_backward_tile(float* X, float* H1, float* H2, float* DQ, const WeightSmem<KP>& w, const NetLayout& lay,
+                                                  float* gs, bool first, const ThreadCoord& tc, const RowMeta* meta, int obs_dim) {
   const int t = threadIdx.x;
   // ---- dW3[o][j] = sum_r dq[r][o] * h2[r][j];  db3[o] = sum_r dq[r][o] --------------------------------------
   {
@@ -162,8 +162,11 @@ __device__ __forceinline__ void mlp_backward_tile(const float* X, float* H1, flo
       for (int j = 0; j < 8; ++j) DQ[tc.wy * kHidden + tn_col(tc, j)] = cs[j];
     }
   }
-  __syncthreads();
+  __syncthreads();  // dh2 (H2 region) is dead from here on: bring the input tile back into it for dW1
+  gather_tile_async<KP>(X, meta, obs_dim);
   if (t < kHidden) rmw(gs + lay.b1 + t, DQ[t] + DQ[kHidden + t] + DQ[2 * kHidden + t] + DQ[3 * kHidden + t], first);
+  cp_async_wait_all();
+  __syncthreads();
   // ---- dW1[m][i] = sum_r dh1[r][m] * x[r][i] ---------------------------------------------------------------------
   {
     const int mg = t >> 4, i0 = t & 15;
@@ -265,9 +268,9 @@ template <int KP, int HEAD>
 __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
   extern __shared__ __align__(16) float smem[];
   WeightSmem<KP> w(smem);
-  float* X = smem + WeightSmem<KP>::kFloats;
-  float* H1 = X + kTileRows * pitch_of<KP>();
+  float* H1 = smem + WeightSmem<KP>::kFloats;
   float* H2 = H1 + kTileRows * kPitchH;
+  float* X = H2;  // the input tile aliases H2: live during layer 1, re-gathered for dW1 once dH2 is dead
   float* Q = H2 + kTileRows * kPitchH;  // network outputs, then dLoss/dOutput, then reduction scratch
   float* carry = Q + kTileRows * kOutPad;  // outputs of the first row of the previously processed (higher) tile
   RowMeta* meta = reinterpret_cast<RowMeta*>(carry + 16);
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
       for (int o = 0; o < kOutPad; ++o) carry[o] = q_first[o];
     }
     __syncthreads();
-    mlp_backward_tile<KP>(X, H1, H2, Q, w, p.lay, gs, first, tc);
+    mlp_backward_tile<KP>(X, H1, H2, Q, w, p.lay, gs, first, tc, meta, p.src.D);
     first = false;
   }
   // ---- per-CTA loss statistics (fixed-order tree: deterministic) ---------------------------------------------------
@@ -415,30 +418,42 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------
-int learner_kernels_init(int in_dim) {
-  MARL_REQUIRE(in_dim >= 1 && in_dim <= 16, "learner kernels: observation width %d not supported yet (1..16)", in_dim);
-  MARL_CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)forward_smem_bytes<16>()));
-  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<16, kHeadDqn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
-  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<16, kHeadA2cCritic>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
-  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<16, kHeadA2cActor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<16>()));
+template <int KP>
+static int init_kp() {
+  MARL_CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)forward_smem_bytes<KP>()));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<KP, kHeadDqn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<KP>()));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<KP, kHeadA2cCritic>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<KP>()));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(train_kernel<KP, kHeadA2cActor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<KP>()));
   return MARL_OK;
 }
 
+int learner_kernels_init(int in_dim) {
+  MARL_REQUIRE(in_dim >= 1 && in_dim <= kMaxObsDim, "learner kernels: observation width %d not supported (1..%d)", in_dim, kMaxObsDim);
+  return in_dim <= 16 ? init_kp<16>() : init_kp<32>();
+}
+
 int launch_mlp_forward(const FwdParams& p, cudaStream_t st) {
-  mlp_forward_kernel<16><<<p.plan.cta_begin[p.plan.n_nets], kMlpThreads, forward_smem_bytes<16>(), st>>>(p);
+  const int grid = p.plan.cta_begin[p.plan.n_nets];
+  if (p.lay.in <= 16) mlp_forward_kernel<16><<<grid, kMlpThreads, forward_smem_bytes<16>(), st>>>(p);
+  else mlp_forward_kernel<32><<<grid, kMlpThreads, forward_smem_bytes<32>(), st>>>(p);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+template <int KP>
+static int launch_train_kp(const TrainParams& p, int head, cudaStream_t st) {
+  const int grid = p.plan.cta_begin[p.plan.n_nets];
+  const size_t sm = train_smem_bytes<KP>();
+  if (head == kHeadDqn) train_kernel<KP, kHeadDqn><<<grid, kMlpThreads, sm, st>>>(p);
+  else if (head == kHeadA2cCritic) train_kernel<KP, kHeadA2cCritic><<<grid, kMlpThreads, sm, st>>>(p);
+  else if (head == kHeadA2cActor) train_kernel<KP, kHeadA2cActor><<<grid, kMlpThreads, sm, st>>>(p);
+  else { set_error("launch_train: unknown head %d", head); return MARL_EINVAL; }
   MARL_CUDA_TRY(cudaGetLastError());
   return MARL_OK;
 }
 
 int launch_train(const TrainParams& p, int head, cudaStream_t st) {
-  const int grid = p.plan.cta_begin[p.plan.n_nets];
-  const size_t sm = train_smem_bytes<16>();
-  if (head == kHeadDqn) train_kernel<16, kHeadDqn><<<grid, kMlpThreads, sm, st>>>(p);
-  else if (head == kHeadA2cCritic) train_kernel<16, kHeadA2cCritic><<<grid, kMlpThreads, sm, st>>>(p);
-  else if (head == kHeadA2cActor) train_kernel<16, kHeadA2cActor><<<grid, kMlpThreads, sm, st>>>(p);
-  else { set_error("launch_train: unknown head %d", head); return MARL_EINVAL; }
-  MARL_CUDA_TRY(cudaGetLastError());
-  return MARL_OK;
+  return p.lay.in <= 16 ? launch_train_kp<16>(p, head, st) : launch_train_kp<32>(p, head, st);
 }
 
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {

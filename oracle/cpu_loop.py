@@ -80,13 +80,13 @@ def _worker(args):
 
 def run_parallel(cfg_kw, batch_size, n_procs, prefill, n_episodes, n_rounds, pool=None):
     """`n_procs` independent single-thread copies of the reference loop (one per host core); returns per-round
-    (total env steps, max seconds over workers)."""
+    (total env steps, max seconds over workers, sum of per-copy rates)."""
     import multiprocessing as mp
 
     ctx = mp.get_context("fork")
     with ctx.Pool(n_procs) as p:
         res = p.map(_worker, [(cfg_kw, batch_size, 1000 + i, prefill, n_episodes, n_rounds) for i in range(n_procs)])
     rounds = []
-    for r in range(n_rounds):
-        rounds.append((sum(w[r][0] for w in res), max(w[r][1] for w in res)))
+    for r in range(n_rounds):  # (total env steps, slowest copy's seconds, sum of the copies' own steps/s)
+        rounds.append((sum(w[r][0] for w in res), max(w[r][1] for w in res), sum(w[r][0] / w[r][1] for w in res)))
     return rounds
