@@ -158,7 +158,7 @@ int launch_grad_reduce(const ReduceParams& p, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
 template <int KP>
-constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + 2 * kTileRows * kPitchH + kTileRows * kOutPad + 16) + RowMeta::kBytes; }
+constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + 2 * kTileRows * kPitchH + kTileRows * kOutPad + 48) + RowMeta::kBytes; }
 template <int KP>
 constexpr size_t train_smem_bytes() { return forward_smem_bytes<KP>(); }
 

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(FwdParams p
   float* H2 = H1 + kTileRows * kPitchH;
   float* X = H2;  // the input tile lives in the H2 region until layer 2 overwrites it
   float* Q = H2 + kTileRows * kPitchH;
-  RowMeta* meta = reinterpret_cast<RowMeta*>(Q + kTileRows * kOutPad + 16);
+  RowMeta* meta = reinterpret_cast<RowMeta*>(Q + kTileRows * kOutPad + 48);
   const ThreadCoord tc;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
@@ -66,29 +66,41 @@ __device__ __forceinline__ void rmw4(float* dst, float4 v, bool first) {
 // beyond the valid ones).  gs = this CTA's gradient partial [P].  Uses DQ as scratch after it is consumed.
 template <int KP>
 __device__ __forceinline__ void mlp_backward_tile(float* X, float* H1, float* H2, float* DQ, const WeightSmem<KP>& w, const NetLayout& lay,
-                                                  float* gs, bool first, const ThreadCoord& tc, const RowMeta* meta, int obs_dim) {
+                                                  float* gs, bool first, const ThreadCoord& tc, const RowMeta* meta, int obs_dim, float* part) {
   const int t = threadIdx.x;
   // ---- dW3[o][j] = sum_r dq[r][o] * h2[r][j];  db3[o] = sum_r dq[r][o] --------------------------------------
   {
     const int j = t & (kHidden - 1), o0 = (t >> 7) * 4;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    float g[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // two interleaved chains per output: half the FMA latency chain
 #pragma unroll 4
-    for (int r = 0; r < kTileRows; ++r) {
-      const float h = at1<kHidden>(H2, r, j);
-      const float4 d = *reinterpret_cast<const float4*>(DQ + r * kOutPad + o0);
-      g0 = fmaf(d.x, h, g0); g1 = fmaf(d.y, h, g1); g2 = fmaf(d.z, h, g2); g3 = fmaf(d.w, h, g3);
+    for (int r = 0; r < kTileRows; r += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float h = at1<kHidden>(H2, r + u, j);
+        const float4 d = *reinterpret_cast<const float4*>(DQ + (r + u) * kOutPad + o0);
+        g[u][0] = fmaf(d.x, h, g[u][0]); g[u][1] = fmaf(d.y, h, g[u][1]); g[u][2] = fmaf(d.z, h, g[u][2]); g[u][3] = fmaf(d.w, h, g[u][3]);
+      }
     }
-    if (o0 + 0 < lay.out) rmw(gs + lay.w3 + (o0 + 0) * kHidden + j, g0, first);
-    if (o0 + 1 < lay.out) rmw(gs + lay.w3 + (o0 + 1) * kHidden + j, g1, first);
-    if (o0 + 2 < lay.out) rmw(gs + lay.w3 + (o0 + 2) * kHidden + j, g2, first);
-    if (o0 + 3 < lay.out) rmw(gs + lay.w3 + (o0 + 3) * kHidden + j, g3, first);
-    if (t < lay.out) {
-      float s = 0.f;
-      for (int r = 0; r < kTileRows; ++r) s += DQ[r * kOutPad + t];
-      rmw(gs + lay.b3 + t, s, first);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (o0 + q < lay.out) rmw(gs + lay.w3 + (o0 + q) * kHidden + j, g[0][q] + g[1][q], first);
+    // db3: one row per lane of the first four warps, shuffle-reduced, four partials combined after the barrier
+    if (t < kTileRows) {
+      const float4 d0 = *reinterpret_cast<const float4*>(DQ + t * kOutPad), d1 = *reinterpret_cast<const float4*>(DQ + t * kOutPad + 4);
+      float v[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[o] += __shfl_xor_sync(0xFFFFFFFFu, v[o], off);
+      }
+      if ((t & 31) == 0) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) part[(t >> 5) * 8 + o] = v[o];
+      }
     }
   }
   __syncthreads();
+  if (t < lay.out) rmw(gs + lay.b3 + t, (part[t] + part[8 + t]) + (part[16 + t] + part[24 + t]), first);
   // ---- dh2[r][j] = (sum_o dq[r][o] * W3[o][j]) * (h2[r][j] > 0), in place over H2; db2 partials ----------------
   float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
   {
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
   float* X = H2;  // the input tile aliases H2: live during layer 1, re-gathered for dW1 once dH2 is dead
   float* Q = H2 + kTileRows * kPitchH;  // network outputs, then dLoss/dOutput, then reduction scratch
   float* carry = Q + kTileRows * kOutPad;  // outputs of the first row of the previously processed (higher) tile
-  RowMeta* meta = reinterpret_cast<RowMeta*>(carry + 16);
+  RowMeta* meta = reinterpret_cast<RowMeta*>(carry + 48);  // carry[16] | db3 partials[32] | row metadata
   const ThreadCoord tc;
   const int t = threadIdx.x;
   int net, row_begin, row_end;
@@ -327,7 +339,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
       for (int o = 0; o < kOutPad; ++o) carry[o] = q_first[o];
     }
     __syncthreads();
-    mlp_backward_tile<KP>(X, H1, H2, Q, w, p.lay, gs, first, tc, meta, p.src.D);
+    mlp_backward_tile<KP>(X, H1, H2, Q, w, p.lay, gs, first, tc, meta, p.src.D, carry + 16);
     first = false;
   }
   // ---- per-CTA loss statistics (fixed-order tree: deterministic) ---------------------------------------------------

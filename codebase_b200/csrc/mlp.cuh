@@ -114,20 +114,21 @@ __device__ __forceinline__ void store_relu_bias(float* __restrict__ out, const f
 // thread t: row = t/2, outputs (t%2)*4 .. +3.  W3 is plain [8][128]; q is plain [128][8].
 __device__ __forceinline__ void head_forward(const float* __restrict__ H, const float* __restrict__ W3, const float* __restrict__ b3, float* __restrict__ q) {
   const int row = threadIdx.x >> 1, o0 = (threadIdx.x & 1) * 4;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // even / odd chunks accumulate separately (shorter FMA chains)
 #pragma unroll 4
-  for (int c = 0; c < kHidden / 4; ++c) {
-    const float4 h = at4<kHidden>(H, row, c);
-    const float4 w0 = reinterpret_cast<const float4*>(W3 + (o0 + 0) * kHidden)[c];
-    const float4 w1 = reinterpret_cast<const float4*>(W3 + (o0 + 1) * kHidden)[c];
-    const float4 w2 = reinterpret_cast<const float4*>(W3 + (o0 + 2) * kHidden)[c];
-    const float4 w3 = reinterpret_cast<const float4*>(W3 + (o0 + 3) * kHidden)[c];
-    s0 = fmaf(h.x, w0.x, s0); s0 = fmaf(h.y, w0.y, s0); s0 = fmaf(h.z, w0.z, s0); s0 = fmaf(h.w, w0.w, s0);
-    s1 = fmaf(h.x, w1.x, s1); s1 = fmaf(h.y, w1.y, s1); s1 = fmaf(h.z, w1.z, s1); s1 = fmaf(h.w, w1.w, s1);
-    s2 = fmaf(h.x, w2.x, s2); s2 = fmaf(h.y, w2.y, s2); s2 = fmaf(h.z, w2.z, s2); s2 = fmaf(h.w, w2.w, s2);
-    s3 = fmaf(h.x, w3.x, s3); s3 = fmaf(h.y, w3.y, s3); s3 = fmaf(h.z, w3.z, s3); s3 = fmaf(h.w, w3.w, s3);
+  for (int c = 0; c < kHidden / 4; c += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float4 h = at4<kHidden>(H, row, c + u);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const float4 w = reinterpret_cast<const float4*>(W3 + (o0 + o) * kHidden)[c + u];
+        s[u][o] = fmaf(h.x, w.x, s[u][o]); s[u][o] = fmaf(h.y, w.y, s[u][o]); s[u][o] = fmaf(h.z, w.z, s[u][o]); s[u][o] = fmaf(h.w, w.w, s[u][o]);
+      }
+    }
   }
-  *reinterpret_cast<float4*>(q + row * kOutPad + o0) = make_float4(s0 + b3[o0], s1 + b3[o0 + 1], s2 + b3[o0 + 2], s3 + b3[o0 + 3]);
+  *reinterpret_cast<float4*>(q + row * kOutPad + o0) =
+      make_float4(s[0][0] + s[1][0] + b3[o0], s[0][1] + s[1][1] + b3[o0 + 1], s[0][2] + s[1][2] + b3[o0 + 2], s[0][3] + s[1][3] + b3[o0 + 3]);
 }
 
 // ---- TN: acc[mi][nj] = sum_r A[r][m] * B[r][n];  m = wy*32 + (mi/4)*16 + ty*4 + mi%4,  n = wx*64 + (nj/4)*32 + tx*4 + nj%4
