@@ -55,6 +55,7 @@ struct marl_a2c {
   float *theta = nullptr, *theta_tgt = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
   float *scratch = nullptr, *loss_part = nullptr, *vt = nullptr, *ret = nullptr, *adv = nullptr, *metrics = nullptr;
   int32_t* idx = nullptr;
+  uint8_t* image = nullptr;  // packed weight images for the tensor-core forward path
   int64_t opt_steps = 0;
 };
 
@@ -64,7 +65,7 @@ int marl_a2c_destroy(marl_a2c* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch); cudaFree(h->loss_part);
-  cudaFree(h->vt); cudaFree(h->ret); cudaFree(h->adv); cudaFree(h->metrics); cudaFree(h->idx);
+  cudaFree(h->vt); cudaFree(h->ret); cudaFree(h->adv); cudaFree(h->metrics); cudaFree(h->idx); cudaFree(h->image);
   delete h;
   return MARL_OK;
 }
@@ -93,9 +94,11 @@ int marl_a2c_create(const marl_mlp_cfg* actor, const marl_mlp_cfg* critic, const
   rc |= dev_alloc_zero(&h->scratch, (size_t)h->n_sm * h->scratch_pitch); rc |= dev_alloc_zero(&h->loss_part, 4 * (size_t)h->n_sm);
   rc |= dev_alloc_zero(&h->vt, rows); rc |= dev_alloc_zero(&h->ret, rows); rc |= dev_alloc_zero(&h->adv, rows); rc |= dev_alloc_zero(&h->metrics, 8);
   rc |= dev_alloc_zero(reinterpret_cast<float**>(&h->idx), max_envs);
+  rc |= dev_alloc_zero(reinterpret_cast<float**>(&h->image), (size_t)(actor->n_nets > critic->n_nets ? actor->n_nets : critic->n_nets) * tc_image_bytes() / 4 + 4);
   if (rc) { marl_a2c_destroy(h); return MARL_ENOMEM; }
   iota_kernel<<<(max_envs + 255) / 256, 256>>>(h->idx, max_envs);
   if (int rc2 = learner_kernels_init(actor->in_dim)) { marl_a2c_destroy(h); return rc2; }
+  if (int rc2 = tc_forward_init()) { marl_a2c_destroy(h); return rc2; }
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("marl_a2c_create: device error during setup"); marl_a2c_destroy(h); return MARL_ECUDA; }
   *out = h;
   return MARL_OK;
@@ -127,7 +130,7 @@ static int a2c_dense_forward(marl_a2c* h, const NetSet& ns, const float* theta, 
   const RowPlan plan = make_plan(ns, n_envs, 1, h->n_sm, 32);
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 0; src.dense = obs; src.E = n_envs; src.N = ns.n_agents; src.D = ns.in;
-  return launch_forward(ns, plan, src, theta, out, (cudaStream_t)stream);
+  return forward_any(ns, plan, src, theta, h->image, out, (cudaStream_t)stream);
 }
 
 /* actor forward of A2CNetwork.act (ac/model.py:148-150): obs float[E][N][in] -> logits float[E][N][n_actions] */
@@ -156,7 +159,7 @@ int marl_a2c_update_grads(marl_a2c* h, const marl_traj_view* batch, int32_t n_en
   const RowPlan cplan = make_plan(h->critic, n_envs, T + 1, h->n_sm, min_units);
   const RowPlan aplan = make_plan(h->actor, n_envs, T + 1, h->n_sm, min_units);
   // 1. target critic on all T+1 observations (ac/model.py:190-193)
-  if (int rc = launch_forward(h->critic, cplan, src, h->theta_tgt, h->vt, st)) return rc;
+  if (int rc = forward_any(h->critic, cplan, src, h->theta_tgt, h->image, h->vt, st)) return rc;
   // 2. n-step returns (ac/model.py:198-201)
   NStepParams np; np.vt = h->vt; np.traj = src.traj; np.idx = h->idx; np.N = N; np.P = n_envs; np.n_steps = h->hp.n_steps; np.ret = h->ret;
   for (int k = 0; k <= h->hp.n_steps; ++k) np.gpow[k] = (float)pow((double)h->hp.gamma, (double)k);

@@ -72,5 +72,6 @@ __host__ __device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t n) {
 __host__ __device__ __forceinline__ float u01(uint32_t u) { return (float)(u >> 8) * (1.0f / 16777216.0f); }
 
 int check_device(int device);
+int tc_forward_enabled();
 
 }  // namespace marl

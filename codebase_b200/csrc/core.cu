@@ -32,9 +32,19 @@ int check_device(int device) {
   return MARL_OK;
 }
 
+static int g_tc_forward = 1;
+int tc_forward_enabled() { return g_tc_forward; }
+
 }  // namespace marl
 
 extern "C" {
+/* Process-wide options.  "tensor_core_forward": 1 = forward-only passes (act, target networks) run on tcgen05 with the
+ * 3xTF32 split (default), 0 = FP32 FFMA kernels. */
+int marl_set_option(const char* name, int32_t value) {
+  if (name && strcmp(name, "tensor_core_forward") == 0) { marl::g_tc_forward = value ? 1 : 0; return MARL_OK; }
+  marl::set_error("marl_set_option: unknown option '%s'", name ? name : "(null)");
+  return MARL_EINVAL;
+}
 int marl_version(void) { return MARL_ABI_VERSION; }
 const char* marl_last_error(void) { return marl::g_err; }
 }

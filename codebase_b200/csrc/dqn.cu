@@ -76,6 +76,7 @@ struct marl_dqn {
   float *theta = nullptr, *theta_tgt = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
   float *scratch = nullptr, *loss_part = nullptr, *tq = nullptr, *q_all = nullptr, *td = nullptr, *loss_dev = nullptr;
   int32_t* idx = nullptr;
+  uint8_t* image = nullptr;  // packed weight images for the tensor-core forward path
   int64_t updates = 0, last_target_update = 0;
   RowPlan train_plan; int n_loss_parts = 0;
   // optional CUDA-event timing of the training kernel (bench.py's roofline leg)
@@ -116,8 +117,10 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   rc |= dqn_alloc(&h->loss_dev, 8);
   if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
+  rc |= dqn_alloc(reinterpret_cast<float**>(&h->image), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
   if (rc) { marl_dqn_destroy(h); return MARL_ENOMEM; }
   if (int rc2 = learner_kernels_init(cfg->in_dim)) { marl_dqn_destroy(h); return rc2; }
+  if (int rc2 = tc_forward_init()) { marl_dqn_destroy(h); return rc2; }
   *out = h;
   return MARL_OK;
 }
@@ -126,7 +129,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
-  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->idx);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->idx); cudaFree(h->image);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -152,7 +155,7 @@ int marl_dqn_forward(marl_dqn* h, const float* obs, int32_t n_envs, int32_t use_
   const RowPlan plan = make_plan(h->ns, n_envs, 1, h->n_sm, 32);
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 0; src.dense = obs; src.E = n_envs; src.N = h->ns.n_agents; src.D = h->ns.in;
-  return launch_forward(h->ns, plan, src, use_target ? h->theta_tgt : h->theta, q_out, (cudaStream_t)stream);
+  return forward_any(h->ns, plan, src, use_target ? h->theta_tgt : h->theta, h->image, q_out, (cudaStream_t)stream);
 }
 
 int marl_replay_sample(uint64_t seed, uint64_t update_idx, int32_t batch, int32_t n_valid, int32_t* idx_out, void* stream) {
@@ -175,12 +178,12 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 1; src.traj = to_view(traj); src.idx = episode_idx; src.N = h->ns.n_agents; src.D = h->ns.in;
   // target network on every gathered row (dqn/model.py:132-134)
-  if (int rc = launch_forward(h->ns, plan, src, h->theta_tgt, h->tq, st)) return rc;
+  if (int rc = forward_any(h->ns, plan, src, h->theta_tgt, h->image, h->tq, st)) return rc;
   int n_loss_parts = plan.cta_begin[plan.n_nets];
   const float* td_ext = nullptr;
   float* loss_part = h->loss_part;
   if (h->hp.mixer == 1) {  // VDN: online Q-values of all agents first, then the agent-summed TD error
-    if (int rc = launch_forward(h->ns, plan, src, h->theta, h->q_all, st)) return rc;
+    if (int rc = forward_any(h->ns, plan, src, h->theta, h->image, h->q_all, st)) return rc;
     VdnTdParams vp; vp.q = h->q_all; vp.tq = h->tq; vp.traj = src.traj; vp.idx = episode_idx; vp.B = batch; vp.N = h->ns.n_agents; vp.A = h->ns.out;
     vp.gamma = h->hp.gamma; vp.double_q = h->hp.double_q; vp.td = h->td;
     const int vb = (batch * T + 255) / 256;

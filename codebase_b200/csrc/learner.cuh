@@ -213,6 +213,24 @@ inline int launch_forward(const NetSet& ns, const RowPlan& plan, const RowSource
   return launch_mlp_forward(fp, st);
 }
 
+// ---- tensor-core forward path (tc_forward.cu) -----------------------------------------------------------------------------
+size_t tc_image_bytes();
+int tc_forward_init();
+int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, uint8_t* image, cudaStream_t st);
+int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st);
+// tc_forward_enabled(): process-wide switch (marl_set_option("tensor_core_forward", 0|1)), declared in common.cuh
+
+// Forward pass through whichever implementation is selected.  `image` is scratch for the packed weights (n_nets images);
+// it is rebuilt from `theta` on every call (3 us) so that it can never go stale against direct parameter writes.
+inline int forward_any(const NetSet& ns, const RowPlan& plan, const RowSource& src, const float* theta, uint8_t* image, float* out, cudaStream_t st) {
+  if (tc_forward_enabled() && image != nullptr) {
+    if (int rc = launch_pack_weights(theta, ns.lay, ns.n_nets, image, st)) return rc;
+    FwdParams fp; fp.plan = plan; fp.src = src; fp.theta = theta; fp.lay = ns.lay; fp.out = out;
+    return launch_tc_forward(fp, image, st);
+  }
+  return launch_forward(ns, plan, src, theta, out, st);
+}
+
 inline int check_mlp_cfg(const marl_mlp_cfg* cfg, const char* who) {
   MARL_REQUIRE(cfg != nullptr, "%s: NULL network config", who);
   MARL_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= MARL_MAX_AGENTS, "%s: n_agents out of range", who);

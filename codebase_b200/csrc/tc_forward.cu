@@ -1,0 +1,285 @@
+// tc_forward.cu -- tcgen05 / TMEM implementation of the forward-only MLP pass (sm_100a).
+//
+// Same contract as mlp_forward_kernel (model.act's network pass, the target-network / target-critic pass of the
+// learners; marlbase/dqn/model.py:99,132-134, marlbase/ac/model.py:148-149,190-193) but the three GEMMs of each 128-row
+// tile run on the 5th-generation tensor cores:
+//   * activations never touch shared memory: thread r owns row r = TMEM lane r; the A operand of every layer is written
+//     with tcgen05.st, the accumulator is read back with tcgen05.ld, bias + ReLU happen in registers;
+//   * weights are the B operand, resident in shared memory as a pre-packed image (K-major, 128-byte swizzle, one
+//     16-KB panel per 32 input features) built once per parameter change by pack_weights_kernel;
+//   * FP32 parity (<= 1e-5) is kept with the error-compensated 3xTF32 split: every operand is stored as
+//     hi = tf32(x) and lo = tf32(x - hi) and each product is accumulated as lo*hi + hi*lo + hi*hi in the FP32 TMEM
+//     accumulator (measured 4e-7 relative on a 128x128x128 product, tools/tc_probe.cu).
+// One elected thread issues tcgen05.mma (kind::tf32, cta_group::1, M = 128, N = 128 or 16); completion reaches the
+// other threads through tcgen05.commit -> mbarrier.
+#include "learner.cuh"
+
+namespace marl {
+
+constexpr int kTcThreads = 128;
+constexpr int kPanelBytes = kHidden * 128;         // 128 rows x 32 floats
+constexpr int kHeadRows = 16;                      // head GEMM uses N = 16 (minimum for M = 128)
+constexpr int kHeadPanelBytes = kHeadRows * 128;
+// image layout (bytes): W1 hi | W1 lo | W2 hi (4 panels) | W2 lo | W3 hi (4 panels of 16 rows) | W3 lo | b1 | b2 | b3
+constexpr int kOffW1Hi = 0, kOffW1Lo = kOffW1Hi + kPanelBytes, kOffW2Hi = kOffW1Lo + kPanelBytes, kOffW2Lo = kOffW2Hi + 4 * kPanelBytes;
+constexpr int kOffW3Hi = kOffW2Lo + 4 * kPanelBytes, kOffW3Lo = kOffW3Hi + 4 * kHeadPanelBytes;
+constexpr int kOffB1 = kOffW3Lo + 4 * kHeadPanelBytes, kOffB2 = kOffB1 + kHidden * 4, kOffB3 = kOffB2 + kHidden * 4;
+constexpr int kImageBytes = kOffB3 + kHeadRows * 4;
+constexpr int kTcSmemBytes = kImageBytes + 64 + 1024;  // + mbarrier / TMEM slot, + slack for 1024-byte alignment
+
+size_t tc_image_bytes() { return kImageBytes; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// ---- weight image --------------------------------------------------------------------------------------------------
+// element (row n, feature k) of a [rows][K] K-major operand -> byte offset inside its panel set
+__device__ __forceinline__ int panel_offset(int n, int k, int panel_bytes) {
+  const int p = k >> 5, c = (k >> 2) & 7, w = k & 3;
+  return p * panel_bytes + n * 128 + ((c ^ (n & 7)) << 4) + (w << 2);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ theta, NetLayout lay, int n_nets, uint8_t* __restrict__ image) {
+  const int net = blockIdx.y;
+  if (net >= n_nets) return;
+  const float* th = theta + (size_t)net * lay.P;
+  uint8_t* img = image + (size_t)net * kImageBytes;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // W1 [128][32] (zero padded beyond in), W2 [128][128], W3 [16][128] (zero rows beyond out)
+  if (i < kHidden * 32) {
+    const int n = i >> 5, k = i & 31;
+    const float x = k < lay.in ? th[lay.w1 + n * lay.in + k] : 0.f, hi = tf32_rn(x);
+    *reinterpret_cast<float*>(img + kOffW1Hi + panel_offset(n, k, kPanelBytes)) = hi;
+    *reinterpret_cast<float*>(img + kOffW1Lo + panel_offset(n, k, kPanelBytes)) = tf32_rn(x - hi);
+  }
+  if (i < kHidden * kHidden) {
+    const int n = i >> 7, k = i & 127;
+    const float x = th[lay.w2 + i], hi = tf32_rn(x);
+    *reinterpret_cast<float*>(img + kOffW2Hi + panel_offset(n, k, kPanelBytes)) = hi;
+    *reinterpret_cast<float*>(img + kOffW2Lo + panel_offset(n, k, kPanelBytes)) = tf32_rn(x - hi);
+  }
+  if (i < kHeadRows * kHidden) {
+    const int n = i >> 7, k = i & 127;
+    const float x = n < lay.out ? th[lay.w3 + n * kHidden + k] : 0.f, hi = tf32_rn(x);
+    *reinterpret_cast<float*>(img + kOffW3Hi + panel_offset(n, k, kHeadPanelBytes)) = hi;
+    *reinterpret_cast<float*>(img + kOffW3Lo + panel_offset(n, k, kHeadPanelBytes)) = tf32_rn(x - hi);
+  }
+  if (i < kHidden) {
+    reinterpret_cast<float*>(img + kOffB1)[i] = th[lay.b1 + i];
+    reinterpret_cast<float*>(img + kOffB2)[i] = th[lay.b2 + i];
+  }
+  if (i < kHeadRows) reinterpret_cast<float*>(img + kOffB3)[i] = i < lay.out ? th[lay.b3 + i] : 0.f;
+}
+
+// ---- tcgen05 helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4, LBO 1, SBO 1024 B,
+// version 1, layout type 2
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128
+__device__ __forceinline__ uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
+               "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+               "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+               : "memory");
+}
+
+// TMEM columns: A hi [0,128), A lo [128,256), D [256,384), head D [384,400)
+constexpr uint32_t kColAHi = 0, kColALo = 128, kColD = 256, kColDHead = 384;
+
+// 3xTF32: D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over `ksteps` steps of 8 features; issued by one thread
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t d_col, const uint8_t* b_hi, const uint8_t* b_lo, int panel_bytes, int ksteps, int n) {
+  const uint32_t idesc = idesc_tf32(n);
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int term = 0; term < 3; ++term) {
+    const uint32_t a_col = term == 0 ? kColALo : kColAHi;
+    const uint8_t* b = term == 1 ? b_lo : b_hi;
+#pragma unroll 1
+    for (int ks = 0; ks < ksteps; ++ks) {
+      mma_tf32_ts(tmem + d_col, tmem + a_col + ks * 8, kmajor_desc(smem_u32(b + (ks >> 2) * panel_bytes + (ks & 3) * 32)), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, const uint8_t* __restrict__ images) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms need 1024-byte alignment
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kImageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int t = threadIdx.x, warp = t >> 5;
+  int net, row_begin, row_end;
+  cta_rows(p.plan, net, row_begin, row_end);
+  if (row_begin >= row_end) return;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (t == 0) mbar_init(bar, 1);
+  {  // the weight image is already in shared-memory layout: straight 16-byte copy
+    const uint4* src = reinterpret_cast<const uint4*>(images + (size_t)net * kImageBytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+#pragma unroll 8
+    for (int i = t; i < kImageBytes / 16; i += kTcThreads) dst[i] = src[i];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const float* b1 = reinterpret_cast<const float*>(smem + kOffB1);
+  const float* b2 = reinterpret_cast<const float*>(smem + kOffB2);
+  const float* b3 = reinterpret_cast<const float*>(smem + kOffB3);
+  const int D = p.src.D, out = p.lay.out;
+  const int k1steps = (D + 7) >> 3;
+  uint32_t parity = 0;
+
+  for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
+    const int nrows = min(kTileRows, row_end - vr0);
+    // ---- input row -> A operand (hi / lo), zero padded to k1steps * 8 features -----------------------------------
+    const float* src = nullptr;
+    size_t dst_row = 0;
+    if (t < nrows) {
+      int agent, unit, off;
+      decode_row(p.plan, net, vr0 + t, agent, unit, off);
+      src = row_ptr(p.src, agent, unit, off);
+      dst_row = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent) : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
+    }
+#pragma unroll 1
+    for (int k0 = 0; k0 < k1steps * 8; k0 += 16) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x = (src != nullptr && k0 + j < D) ? src[k0 + j] : 0.f;
+        hi[j] = tf32_rn(x); lo[j] = tf32_rn(x - hi[j]);
+      }
+      tmem_st16(lane_base + kColAHi + k0, hi);
+      tmem_st16(lane_base + kColALo + k0, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1 -------------------------------------------------------------------------------------------------
+    if (t == 0) {
+      tc_fence_after();
+      issue_layer(tmem, kColD, smem + kOffW1Hi, smem + kOffW1Lo, kPanelBytes, k1steps, kHidden);
+      mma_commit(bar);
+    }
+    mbar_wait(bar, parity); parity ^= 1;
+    tc_fence_after();
+    // ---- bias + ReLU, next A operand (twice: after layer 1 and after layer 2) ------------------------------------------
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+      const float* bias = layer == 0 ? b1 : b2;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kHidden; c0 += 16) {
+        float v[16], hi[16], lo[16];
+        tmem_ld16(lane_base + kColD + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float h = fmaxf(v[j] + bias[c0 + j], 0.f);
+          hi[j] = tf32_rn(h); lo[j] = tf32_rn(h - hi[j]);
+        }
+        tmem_st16(lane_base + kColAHi + c0, hi);
+        tmem_st16(lane_base + kColALo + c0, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncthreads();
+      if (t == 0) {
+        tc_fence_after();
+        if (layer == 0) issue_layer(tmem, kColD, smem + kOffW2Hi, smem + kOffW2Lo, kPanelBytes, kHidden / 8, kHidden);
+        else issue_layer(tmem, kColDHead, smem + kOffW3Hi, smem + kOffW3Lo, kHeadPanelBytes, kHidden / 8, kHeadRows);
+        mma_commit(bar);
+      }
+      mbar_wait(bar, parity); parity ^= 1;
+      tc_fence_after();
+    }
+    // ---- head epilogue: outputs to global -------------------------------------------------------------------------------
+    {
+      float v[16];
+      tmem_ld16(lane_base + kColDHead, v);
+      if (t < nrows) {
+        float* dst = p.out + dst_row * out;
+        for (int o = 0; o < out; ++o) dst[o] = v[o] + b3[o];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // every lane has consumed D before the next tile's MMAs overwrite it
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------------------------
+int tc_forward_init() {
+  MARL_CUDA_TRY(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  return MARL_OK;
+}
+
+int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, uint8_t* image, cudaStream_t st) {
+  dim3 grid((kHidden * kHidden + 255) / 256, n_nets);
+  pack_weights_kernel<<<grid, 256, 0, st>>>(theta, lay, n_nets, image);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st) {
+  tc_forward_kernel<<<p.plan.cta_begin[p.plan.n_nets], kTcThreads, kTcSmemBytes, st>>>(p, images);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+}  // namespace marl

@@ -32,6 +32,8 @@ extern "C" {
 
 int marl_version(void);
 const char* marl_last_error(void);
+/* Process-wide options: "tensor_core_forward" 1 (default) = forward-only passes on tcgen05 with the 3xTF32 split, 0 = FP32 FFMA. */
+int marl_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------------
  * Level-Based Foraging, E environments per handle, one transition of all of them per launch.
