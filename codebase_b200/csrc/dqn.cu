@@ -76,7 +76,9 @@ struct marl_dqn {
   float *theta = nullptr, *theta_tgt = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
   float *scratch = nullptr, *loss_part = nullptr, *tq = nullptr, *q_all = nullptr, *td = nullptr, *loss_dev = nullptr;
   int32_t* idx = nullptr;
-  uint8_t* image = nullptr;  // packed weight images for the tensor-core forward path
+  uint8_t* image = nullptr;      // packed weight images for the tensor-core forward path (scratch, rebuilt per call)
+  uint8_t* image_tgt = nullptr;  // image of theta_tgt, rebuilt only when the target network changed
+  bool tgt_image_current = false;
   int64_t updates = 0, last_target_update = 0;
   RowPlan train_plan; int n_loss_parts = 0;
   // optional CUDA-event timing of the training kernel (bench.py's roofline leg)
@@ -118,6 +120,7 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->image), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
+  rc |= dqn_alloc(reinterpret_cast<float**>(&h->image_tgt), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
   if (rc) { marl_dqn_destroy(h); return MARL_ENOMEM; }
   if (int rc2 = learner_kernels_init(cfg->in_dim)) { marl_dqn_destroy(h); return rc2; }
   if (int rc2 = tc_forward_init()) { marl_dqn_destroy(h); return rc2; }
@@ -129,7 +132,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
-  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->idx); cudaFree(h->image);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -146,6 +149,7 @@ int marl_dqn_sync_target(marl_dqn* h, void* stream) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_sync_target: NULL handle");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   MARL_CUDA_TRY(cudaMemcpyAsync(h->theta_tgt, h->theta, h->n_params * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->tgt_image_current = false;
   return MARL_OK;
 }
 
@@ -178,7 +182,8 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 1; src.traj = to_view(traj); src.idx = episode_idx; src.N = h->ns.n_agents; src.D = h->ns.in;
   // target network on every gathered row (dqn/model.py:132-134)
-  if (int rc = forward_any(h->ns, plan, src, h->theta_tgt, h->image, h->tq, st)) return rc;
+  if (int rc = forward_any(h->ns, plan, src, h->theta_tgt, h->image_tgt, h->tq, st, h->tgt_image_current)) return rc;
+  h->tgt_image_current = tc_forward_enabled() != 0;
   int n_loss_parts = plan.cta_begin[plan.n_nets];
   const float* td_ext = nullptr;
   float* loss_part = h->loss_part;
@@ -219,6 +224,7 @@ int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   ap.target_mode = 0; ap.tau = tu; ap.tgt_begin = 0; ap.tgt_n = (int)h->n_params;
   if (tu > 1.0f && (float)(h->updates - h->last_target_update) >= tu) { ap.target_mode = 1; h->last_target_update = h->updates; }
   else if (tu < 1.0f) ap.target_mode = 2;
+  if (ap.target_mode != 0) h->tgt_image_current = false;  // theta_tgt changes in this launch
   ap.loss_out = loss_out ? loss_out : h->loss_dev;
   return launch_adam(ap, (cudaStream_t)stream);
 }
@@ -260,6 +266,14 @@ int marl_dqn_timing(marl_dqn* h, int32_t enable, float* total_ms, int32_t* count
   }
   if (total_ms) *total_ms = tot;
   if (count) *count = h->ev_used;
+  return MARL_OK;
+}
+
+/* Tell the library that the caller wrote to the parameter buffers returned by marl_dqn_param_ptrs (cached derived data --
+ * the packed tensor-core image of the target network -- is rebuilt on next use). */
+int marl_dqn_params_changed(marl_dqn* h) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_params_changed: NULL handle");
+  h->tgt_image_current = false;
   return MARL_OK;
 }
 

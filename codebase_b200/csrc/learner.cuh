@@ -222,9 +222,11 @@ int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st
 
 // Forward pass through whichever implementation is selected.  `image` is scratch for the packed weights (n_nets images);
 // it is rebuilt from `theta` on every call (3 us) so that it can never go stale against direct parameter writes.
-inline int forward_any(const NetSet& ns, const RowPlan& plan, const RowSource& src, const float* theta, uint8_t* image, float* out, cudaStream_t st) {
+inline int forward_any(const NetSet& ns, const RowPlan& plan, const RowSource& src, const float* theta, uint8_t* image, float* out, cudaStream_t st,
+                       bool image_is_current = false) {
   if (tc_forward_enabled() && image != nullptr) {
-    if (int rc = launch_pack_weights(theta, ns.lay, ns.n_nets, image, st)) return rc;
+    if (!image_is_current)
+      if (int rc = launch_pack_weights(theta, ns.lay, ns.n_nets, image, st)) return rc;
     FwdParams fp; fp.plan = plan; fp.src = src; fp.theta = theta; fp.lay = ns.lay; fp.out = out;
     return launch_tc_forward(fp, image, st);
   }

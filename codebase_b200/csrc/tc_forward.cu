@@ -118,9 +118,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
                  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                : "r"(addr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// issue only; the caller waits with tmem_ld_wait() before touching r[]
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(addr));
+}
+// the registers are in/out operands of the wait so that no use of them can be scheduled ahead of it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
@@ -165,11 +184,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) mbar_init(bar, 1);
-  {  // the weight image is already in shared-memory layout: straight 16-byte copy
-    const uint4* src = reinterpret_cast<const uint4*>(images + (size_t)net * kImageBytes);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-#pragma unroll 8
-    for (int i = t; i < kImageBytes / 16; i += kTcThreads) dst[i] = src[i];
+  {  // the weight image is already in shared-memory layout: asynchronous 16-byte copies, all in flight at once
+    const uint8_t* src = images + (size_t)net * kImageBytes;
+    const uint32_t dst = smem_u32(smem);
+#pragma unroll 4
+    for (int i = t; i < kImageBytes / 16; i += kTcThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
   tc_fence_before();
@@ -183,28 +204,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
   const int D = p.src.D, out = p.lay.out;
   const int k1steps = (D + 7) >> 3;
   uint32_t parity = 0;
-
-  for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
-    const int nrows = min(kTileRows, row_end - vr0);
-    // ---- input row -> A operand (hi / lo), zero padded to k1steps * 8 features -----------------------------------
+  // this thread's input row of the current tile (prefetched one tile ahead) and where its outputs go
+  float xin[kMaxObsDim];
+  size_t dst_row = 0, dst_next = 0;
+  auto fetch_row = [&](int vr0, int nrows, size_t& dst) {
     const float* src = nullptr;
-    size_t dst_row = 0;
     if (t < nrows) {
       int agent, unit, off;
       decode_row(p.plan, net, vr0 + t, agent, unit, off);
       src = row_ptr(p.src, agent, unit, off);
-      dst_row = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent) : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
+      dst = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent) : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
     }
-#pragma unroll 1
-    for (int k0 = 0; k0 < k1steps * 8; k0 += 16) {
-      float hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x = (src != nullptr && k0 + j < D) ? src[k0 + j] : 0.f;
-        hi[j] = tf32_rn(x); lo[j] = tf32_rn(x - hi[j]);
+    for (int j = 0; j < kMaxObsDim; ++j) xin[j] = (src != nullptr && j < D) ? src[j] : 0.f;
+  };
+  fetch_row(row_begin, min(kTileRows, row_end - row_begin), dst_row);
+
+  for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
+    const int nrows = min(kTileRows, row_end - vr0);
+    // ---- input row -> A operand (hi / lo), zero padded to k1steps * 8 features -----------------------------------
+#pragma unroll
+    for (int k0 = 0; k0 < kMaxObsDim; k0 += 16) {
+      if (k0 < k1steps * 8) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { hi[j] = tf32_rn(xin[k0 + j]); lo[j] = tf32_rn(xin[k0 + j] - hi[j]); }
+        tmem_st16(lane_base + kColAHi + k0, hi);
+        tmem_st16(lane_base + kColALo + k0, lo);
       }
-      tmem_st16(lane_base + kColAHi + k0, hi);
-      tmem_st16(lane_base + kColALo + k0, lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
@@ -215,23 +242,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
       issue_layer(tmem, kColD, smem + kOffW1Hi, smem + kOffW1Lo, kPanelBytes, k1steps, kHidden);
       mma_commit(bar);
     }
+    // prefetch the next tile's rows: the loads stay in flight under this tile's epilogues and MMAs
+    if (vr0 + kTileRows < row_end) fetch_row(vr0 + kTileRows, min(kTileRows, row_end - vr0 - kTileRows), dst_next);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
     // ---- bias + ReLU, next A operand (twice: after layer 1 and after layer 2) ------------------------------------------
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
       const float* bias = layer == 0 ? b1 : b2;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kHidden; c0 += 16) {
-        float v[16], hi[16], lo[16];
-        tmem_ld16(lane_base + kColD + c0, v);
+      // software pipeline over 16-column chunks: the TMEM load of chunk c+1 is in flight while chunk c is processed
+      uint32_t ra[16], rb[16];
+      tmem_ld16_issue(lane_base + kColD, ra);
+      tmem_ld_wait(ra);
+#pragma unroll
+      for (int c = 0; c < kHidden / 16; ++c) {
+        uint32_t (&cur)[16] = (c & 1) ? rb : ra;
+        uint32_t (&nxt)[16] = (c & 1) ? ra : rb;
+        if (c + 1 < kHidden / 16) tmem_ld16_issue(lane_base + kColD + 16 * (c + 1), nxt);
+        float hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float h = fmaxf(v[j] + bias[c0 + j], 0.f);
+          const float h = fmaxf(__uint_as_float(cur[j]) + bias[16 * c + j], 0.f);
           hi[j] = tf32_rn(h); lo[j] = tf32_rn(h - hi[j]);
         }
-        tmem_st16(lane_base + kColAHi + c0, hi);
-        tmem_st16(lane_base + kColALo + c0, lo);
+        tmem_st16(lane_base + kColAHi + 16 * c, hi);
+        tmem_st16(lane_base + kColALo + 16 * c, lo);
+        if (c + 1 < kHidden / 16) tmem_ld_wait(nxt);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -254,6 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
         for (int o = 0; o < out; ++o) dst[o] = v[o] + b3[o];
       }
     }
+    dst_row = dst_next;
     tc_fence_before();
     __syncthreads();  // every lane has consumed D before the next tile's MMAs overwrite it
     tc_fence_after();

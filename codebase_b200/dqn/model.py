@@ -196,6 +196,10 @@ class QNetwork:
     def hard_update(self):
         nat.check(self._lib.marl_dqn_sync_target(self._h, nat.stream_ptr()), "marl_dqn_sync_target")
 
+    def params_changed(self):
+        """Call after writing `theta` / `theta_tgt` directly (checkpoint load, tests): cached derived data is rebuilt."""
+        nat.check(self._lib.marl_dqn_params_changed(self._h), "marl_dqn_params_changed")
+
     def state_dict(self):
         sd = flat_to_state_dict(self.theta.detach().cpu(), f"critic.{self._kind}", self.n_nets, self.in_dim, self.n_actions)
         sd.update(flat_to_state_dict(self.theta_tgt.detach().cpu(), f"target.{self._kind}", self.n_nets, self.in_dim, self.n_actions))
@@ -204,6 +208,7 @@ class QNetwork:
     def load_state_dict(self, sd):
         self.theta.copy_(state_dict_to_flat(sd, f"critic.{self._kind}", self.n_nets))
         self.theta_tgt.copy_(state_dict_to_flat(sd, f"target.{self._kind}", self.n_nets))
+        self.params_changed()
 
     def parameters(self):
         return [self.theta]

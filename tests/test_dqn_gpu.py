@@ -117,6 +117,7 @@ def test_update_matches_oracle_on_random_batches(mixer, sharing, B, n_agents):
         assert np.quantile(d, 0.999) < 1e-5 and d.max() < 2 * hp.lr * (u + 1) + 1e-6
         # keep the two trajectories glued so that later steps compare like for like
         m.theta.copy_(st.theta); m.theta_tgt.copy_(st.theta_tgt); m.adam_m.copy_(st.m); m.adam_v.copy_(st.v)
+        m.params_changed()  # direct writes: cached derived data (packed target image) must be rebuilt
     assert m.updates == 3
 
 
