@@ -153,18 +153,24 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
 // TMEM columns: A hi [0,128), A lo [128,256), D [256,384), head D [384,400)
 constexpr uint32_t kColAHi = 0, kColALo = 128, kColD = 256, kColDHead = 384;
 
-// 3xTF32: D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over `ksteps` steps of 8 features; issued by one thread
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t d_col, const uint8_t* b_hi, const uint8_t* b_lo, int panel_bytes, int ksteps, int n) {
-  const uint32_t idesc = idesc_tf32(n);
-  uint32_t acc = 0;
-#pragma unroll 1
+// 3xTF32: D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over KSTEPS steps of 8 features; issued by one thread.
+// Fully unrolled: every operand address is base + compile-time constant (the descriptor's address field counts
+// 16-byte units, so advancing by b bytes is desc + (b >> 4)); the issuing thread spends a handful of instructions per
+// MMA and the tensor pipe, not the issue loop, sets the pace.
+template <int KSTEPS, int N, int PANEL_BYTES>
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t d_col, uint32_t b_hi_addr, uint32_t b_lo_addr, int ksteps_rt) {
+  const uint32_t idesc = idesc_tf32(N);
+  const uint64_t dhi = kmajor_desc(b_hi_addr), dlo = kmajor_desc(b_lo_addr);
+  const uint32_t d = tmem + d_col, ahi = tmem + kColAHi, alo = tmem + kColALo;
+#pragma unroll
   for (int term = 0; term < 3; ++term) {
-    const uint32_t a_col = term == 0 ? kColALo : kColAHi;
-    const uint8_t* b = term == 1 ? b_lo : b_hi;
-#pragma unroll 1
-    for (int ks = 0; ks < ksteps; ++ks) {
-      mma_tf32_ts(tmem + d_col, tmem + a_col + ks * 8, kmajor_desc(smem_u32(b + (ks >> 2) * panel_bytes + (ks & 3) * 32)), idesc, acc);
-      acc = 1;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      if (ks < ksteps_rt) {
+        constexpr int kDummy = 0; (void)kDummy;
+        const uint32_t off16 = (uint32_t)(((ks >> 2) * PANEL_BYTES + (ks & 3) * 32) >> 4);
+        mma_tf32_ts(d, (term == 0 ? alo : ahi) + ks * 8, (term == 1 ? dlo : dhi) + off16, idesc, (term | ks) ? 1u : 0u);
+      }
     }
   }
 }
@@ -197,6 +203,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   const float* b1 = reinterpret_cast<const float*>(smem + kOffB1);
   const float* b2 = reinterpret_cast<const float*>(smem + kOffB2);
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
     // ---- layer 1 -------------------------------------------------------------------------------------------------
     if (t == 0) {
       tc_fence_after();
-      issue_layer(tmem, kColD, smem + kOffW1Hi, smem + kOffW1Lo, kPanelBytes, k1steps, kHidden);
+      issue_layer<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
       mma_commit(bar);
     }
     // prefetch the next tile's rows: the loads stay in flight under this tile's epilogues and MMAs
@@ -274,8 +281,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
       __syncthreads();
       if (t == 0) {
         tc_fence_after();
-        if (layer == 0) issue_layer(tmem, kColD, smem + kOffW2Hi, smem + kOffW2Lo, kPanelBytes, kHidden / 8, kHidden);
-        else issue_layer(tmem, kColDHead, smem + kOffW3Hi, smem + kOffW3Lo, kHeadPanelBytes, kHidden / 8, kHeadRows);
+        if (layer == 0) issue_layer<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
+        else issue_layer<kHidden / 8, kHeadRows, kHeadPanelBytes>(tmem, kColDHead, smem_base + kOffW3Hi, smem_base + kOffW3Lo, kHidden / 8);
         mma_commit(bar);
       }
       mbar_wait(bar, parity); parity ^= 1;
