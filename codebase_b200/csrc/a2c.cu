@@ -170,7 +170,7 @@ int marl_a2c_update_grads(marl_a2c* h, const marl_traj_view* batch, int32_t n_en
   tp.plan = cplan; tp.src = src; tp.theta = h->theta + h->n_actor; tp.lay = h->critic.lay; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch;
   tp.loss_part = h->loss_part; tp.returns = h->ret; tp.adv_out = h->adv; tp.value_coef = h->hp.value_loss_coef;
   if (int rc = launch_train(tp, kHeadA2cCritic, st)) return rc;
-  ReduceParams rp; memset(&rp, 0, sizeof(rp));
+  ReduceParams rp; memset(&rp, 0, sizeof(rp));  // (sumsq_part stays NULL: two passes write different gradient slices)
   rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->critic.n_nets; rp.P = h->critic.lay.P; rp.scratch_pitch = h->scratch_pitch;
   memcpy(rp.cta_begin, cplan.cta_begin, sizeof(rp.cta_begin));
   rp.n_loss_parts = cplan.cta_begin[cplan.n_nets]; rp.grad = h->grad + h->n_actor; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0;

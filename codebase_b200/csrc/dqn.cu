@@ -74,7 +74,8 @@ struct marl_dqn {
   int64_t n_params = 0;  // n_nets * P
   int scratch_pitch = 0;
   float *theta = nullptr, *theta_tgt = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
-  float *scratch = nullptr, *loss_part = nullptr, *tq = nullptr, *q_all = nullptr, *td = nullptr, *loss_dev = nullptr;
+  float *scratch = nullptr, *loss_part = nullptr, *tq = nullptr, *q_all = nullptr, *td = nullptr, *loss_dev = nullptr, *sumsq = nullptr;
+  bool grads_are_local = false;  // set by update_grads, cleared when the caller may have all-reduced grad
   int32_t* idx = nullptr;
   uint8_t* image = nullptr;      // packed weight images for the tensor-core forward path (scratch, rebuilt per call)
   uint8_t* image_tgt = nullptr;  // image of theta_tgt, rebuilt only when the target network changed
@@ -117,6 +118,7 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   rc |= dqn_alloc(&h->loss_part, 4 * ((size_t)h->n_sm + (size_t)max_batch * max_T / 256 + 2));
   rc |= dqn_alloc(&h->tq, rows * cfg->out_dim);
   rc |= dqn_alloc(&h->loss_dev, 8);
+  rc |= dqn_alloc(&h->sumsq, (size_t)(h->n_params + 63) / 64 + 1);
   if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->image), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
@@ -132,7 +134,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
-  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -207,7 +209,7 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   if (rec) { cudaEventRecord(h->ev[2 * h->ev_used + 1], st); h->ev_used += 1; }
   ReduceParams rp; rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->ns.n_nets; rp.P = h->ns.lay.P; rp.scratch_pitch = h->scratch_pitch;
   memcpy(rp.cta_begin, plan.cta_begin, sizeof(rp.cta_begin));
-  rp.n_loss_parts = n_loss_parts; rp.grad = h->grad; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0;
+  rp.n_loss_parts = n_loss_parts; rp.grad = h->grad; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0; rp.sumsq_part = h->sumsq;
   return launch_grad_reduce(rp, st);
 }
 
@@ -215,7 +217,7 @@ int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_update_apply: NULL handle");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   h->updates += 1;
-  AdamParams ap; ap.theta = h->theta; ap.theta_tgt = h->theta_tgt; ap.m = h->m; ap.v = h->v; ap.grad = h->grad; ap.n = (int)h->n_params;
+  AdamParams ap; memset(&ap, 0, sizeof(ap)); ap.theta = h->theta; ap.theta_tgt = h->theta_tgt; ap.m = h->m; ap.v = h->v; ap.grad = h->grad; ap.n = (int)h->n_params;
   ap.lr = h->hp.lr; ap.beta1 = h->hp.beta1; ap.beta2 = h->hp.beta2; ap.eps = h->hp.eps; ap.grad_clip = h->hp.grad_clip;
   ap.bc1 = (float)(1.0 - pow((double)h->hp.beta1, (double)h->updates));
   ap.bc2_sqrt = (float)sqrt(1.0 - pow((double)h->hp.beta2, (double)h->updates));
@@ -226,11 +228,14 @@ int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   else if (tu < 1.0f) ap.target_mode = 2;
   if (ap.target_mode != 0) h->tgt_image_current = false;  // theta_tgt changes in this launch
   ap.loss_out = loss_out ? loss_out : h->loss_dev;
+  ap.sumsq_part = h->grads_are_local ? h->sumsq : nullptr; ap.n_sumsq = (int)((h->n_params + 63) / 64);
+  h->grads_are_local = false;
   return launch_adam(ap, (cudaStream_t)stream);
 }
 
 int marl_dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, float* loss_out, void* stream) {
   if (int rc = marl_dqn_update_grads(h, traj, episode_idx, batch, stream)) return rc;
+  h->grads_are_local = true;  // nobody touched grad between the two halves: the clip can use the reduce kernel's sums of squares
   return marl_dqn_update_apply(h, loss_out, stream);
 }
 

@@ -137,6 +137,7 @@ struct ReduceParams {
   float* grad;       // [n_nets*P] gradient sums of this network set
   float* stats;      // [4] sums of the loss parts (NULL: skip)
   int stats_accumulate;  // add to stats instead of overwriting (second pass of an actor-critic update)
+  float* sumsq_part;     // [ceil(n_nets*P / 64)] per-block sum of squares of the reduced gradients (NULL: skip)
 };
 
 struct AdamParams {
@@ -148,6 +149,7 @@ struct AdamParams {
   int target_mode;  // 0 none, 1 hard copy, 2 polyak
   float tau;
   float* loss_out;  // [6]: stats[0]/filled, grad norm, stats[2]/filled, stats[3]/filled, filled, 0
+  const float* sumsq_part; int n_sumsq;  // optional per-block sums of squares of grad[0..n) (local gradients only: single GPU)
 };
 
 // host-side launchers (defined next to the kernels in learner_kernels.cu); return MARL_* codes

@@ -359,28 +359,47 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void grad_reduce_kernel(ReduceParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = p.n_nets * p.P;
+// 64 parameters x 4 CTA-slices per block: slice q sums the partials of CTAs c0+q, c0+q+4, ... (four loads in flight per
+// thread), the four slices are combined in a fixed order through shared memory -> deterministic.  Each block also
+// leaves the sum of squares of its 64 reduced gradients in sumsq_part (single-GPU fast path of the clip in adam_kernel).
+__global__ void __launch_bounds__(256) grad_reduce_kernel(ReduceParams p) {
+  __shared__ float part[4][64];
+  __shared__ float sq[64];
+  const int lane = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + lane, n = p.n_nets * p.P;
+  float s = 0.f;
   if (i < n) {
     const int net = i / p.P, j = i - net * p.P;
-    // fixed association (four interleaved chains, then a fixed combine): deterministic, and the loads overlap
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     const int c0 = p.cta_begin[net], c1 = p.cta_begin[net + 1];
     const float* base = p.scratch + j;
-    int c = c0;
-#pragma unroll 2
-    for (; c + 3 < c1; c += 4) {
-      s0 += base[(size_t)c * p.scratch_pitch]; s1 += base[(size_t)(c + 1) * p.scratch_pitch];
-      s2 += base[(size_t)(c + 2) * p.scratch_pitch]; s3 += base[(size_t)(c + 3) * p.scratch_pitch];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = c0 + q;
+    for (; c + 12 < c1; c += 16) {
+      a0 += base[(size_t)c * p.scratch_pitch]; a1 += base[(size_t)(c + 4) * p.scratch_pitch];
+      a2 += base[(size_t)(c + 8) * p.scratch_pitch]; a3 += base[(size_t)(c + 12) * p.scratch_pitch];
     }
-    for (; c < c1; ++c) s0 += base[(size_t)c * p.scratch_pitch];
-    p.grad[i] = (s0 + s1) + (s2 + s3);
-  } else if (i < n + 4 && p.stats) {
-    const int which = i - n;
-    float s = p.stats_accumulate ? p.stats[which] : 0.f;
-    for (int c = 0; c < p.n_loss_parts; ++c) s += p.loss_part[4 * c + which];
-    p.stats[which] = s;
+    for (; c < c1; c += 4) a0 += base[(size_t)c * p.scratch_pitch];
+    s = (a0 + a1) + (a2 + a3);
+  }
+  part[q][lane] = s;
+  __syncthreads();
+  if (q == 0) {
+    const float g = (part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]);
+    if (i < n) p.grad[i] = g;
+    sq[lane] = (i < n) ? g * g : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = sq[threadIdx.x] + sq[threadIdx.x + 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+    if (threadIdx.x == 0 && p.sumsq_part) p.sumsq_part[blockIdx.x] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 68 && p.stats) {
+    const int which = threadIdx.x - 64;
+    float t = p.stats_accumulate ? p.stats[which] : 0.f;
+    for (int c = 0; c < p.n_loss_parts; ++c) t += p.loss_part[4 * c + which];
+    p.stats[which] = t;
   }
 }
 
@@ -391,7 +410,15 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
   __shared__ float red[256];
   const float inv_fill = 1.f / p.grad[p.n + 1];
   float clip = 1.f, norm = 0.f;
-  {
+  if (p.sumsq_part) {  // single-GPU: grad_reduce_kernel already left per-block sums of squares (fixed-order combine)
+    float s = 0.f;
+    for (int i = threadIdx.x; i < p.n_sumsq; i += 256) s += p.sumsq_part[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+    norm = sqrtf(red[0]) * inv_fill;
+    if (p.grad_clip > 0.f) clip = fminf(p.grad_clip / (norm + 1e-6f), 1.f);
+  } else {
     float s = 0.f;
     const int n4 = p.n >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(p.grad);
@@ -469,8 +496,8 @@ int launch_train(const TrainParams& p, int head, cudaStream_t st) {
 }
 
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
-  const int n = p.n_nets * p.P + 4;
-  grad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p);
+  const int n = p.n_nets * p.P;
+  grad_reduce_kernel<<<(n + 63) / 64, 256, 0, st>>>(p);
   MARL_CUDA_TRY(cudaGetLastError());
   return MARL_OK;
 }
