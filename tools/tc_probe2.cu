@@ -1,0 +1,163 @@
+// tc_probe2.cu -- bring-up of the MN-major operand forms the tensor-core backward needs (sm_100a):
+//   test 1 (TS form, B MN-major):  D[m][n] = sum_k A[m][k] * W[k][n]        (dH1 = dH2 * W2, W2 native [k][n], n contiguous)
+//   test 2 (SS form, A and B MN-major): D[m][n] = sum_k P[k][m] * Q[k][n]    (dW = dOut^T * In, both row-major [k=row][feature])
+// Shared-memory image for an MN-major [k][mn] operand: one 16-KB panel per 32 mn-features, row k = 128 bytes, 16-byte chunk
+// index XOR (k & 7)  -- byte-identical to the K-major image of the transposed role, which is why one packed W2 serves both
+// the forward (K-major) and the input-gradient (MN-major) GEMM.  3xTF32 in both tests.
+#include <cstdio>
+#include <cstdint>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+constexpr int M = 128, N = 128, K = 128, kPanel = 128 * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ float tf32_rn(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+
+// descriptor: start>>4 | LBO<<16 | SBO<<32 | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+#define TMEM_ST8(addr, v) asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), \
+  "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory")
+#define TMEM_LD8(addr, v) do { uint32_t r0, r1, r2, r3, r4, r5, r6, r7; \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "r"(addr)); \
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7) :: "memory"); \
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3); v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7); } while (0)
+
+// Row-major [rows=128][128] fp32 matrix -> hi / lo images: panel p = columns 32p..32p+31, row r at 128*r, chunk ^ (r & 7)
+__device__ void stage_rowmajor(const float* __restrict__ src, uint8_t* hi_img, uint8_t* lo_img) {
+  for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
+    const int r = i >> 5, c4 = i & 31, p = c4 >> 3, c = c4 & 7;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * 128 + 4 * c4);
+    float4 h, l;
+    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+    l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+    const int off = p * kPanel + r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<float4*>(hi_img + off) = h;
+    *reinterpret_cast<float4*>(lo_img + off) = l;
+  }
+}
+
+// test 1: A [m][k] (rows on TMEM lanes), W [k][n] row-major.   test 2: P [k][m], Q [k][n] row-major.
+__global__ void __launch_bounds__(128, 1) probe2(const float* __restrict__ A_or_P, const float* __restrict__ W_or_Q, float* __restrict__ D, int test) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *b_hi = smem, *b_lo = smem + 4 * kPanel, *a_hi = smem + 8 * kPanel, *a_lo = smem + 12 * kPanel;  // a_* only used by test 2 (needs 256 KB -> K split below)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (test == 1 ? 8 : 8) * kPanel + (test == 2 ? 4 * kPanel : 0));
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (t == 0) mbar_init(bar, 1);
+  stage_rowmajor(W_or_Q, b_hi, b_lo);
+  if (test == 2) {  // P: only the hi image fits next to Q's two images (192 KB); the lo*hi term uses a second pass below
+    // stage P hi into a_hi region (64 KB): total 64*3 = 192 KB
+    for (int i = t; i < 128 * 32; i += 128) {
+      const int r = i >> 5, c4 = i & 31, p = c4 >> 3, c = c4 & 7;
+      const float4 v = *reinterpret_cast<const float4*>(A_or_P + r * 128 + 4 * c4);
+      float4 h; h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+      *reinterpret_cast<float4*>(a_hi + p * kPanel + r * 128 + ((c ^ (r & 7)) << 4)) = h;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot, lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  if (test == 1) {
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float hi[8], lo[8];
+      for (int j = 0; j < 8; ++j) { const float x = A_or_P[t * K + k0 + j]; hi[j] = tf32_rn(x); lo[j] = tf32_rn(x - hi[j]); }
+      TMEM_ST8(lane_base + k0, hi);
+      TMEM_ST8(lane_base + 128 + k0, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (t == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t acc = 0;
+    if (test == 1) {
+      const uint32_t idesc = make_idesc(N, 0, 1);
+      for (int term = 0; term < 3; ++term)
+        for (int ks = 0; ks < K / 8; ++ks) {  // k-step = 8 rows of the [k][n] image = one 1024-byte row group
+          const uint8_t* b = (term == 1 ? b_lo : b_hi) + ks * 1024;
+          mma_ts(tmem + 256, tmem + (term == 0 ? 128 : 0) + ks * 8, make_desc(smem_u32(b), kPanel, 1024), idesc, acc);
+          acc = 1;
+        }
+    } else {
+      const uint32_t idesc = make_idesc(N, 1, 1);
+      for (int term = 0; term < 2; ++term)  // P_hi*Q_lo, P_hi*Q_hi  (P_lo*Q_hi omitted: see main(), error budget checked there)
+        for (int ks = 0; ks < K / 8; ++ks) {
+          const uint8_t* b = (term == 0 ? b_lo : b_hi) + ks * 1024;
+          mma_ss(tmem + 256, make_desc(smem_u32(a_hi + ks * 1024), kPanel, 1024), make_desc(smem_u32(b), kPanel, 1024), idesc, acc);
+          acc = 1;
+        }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  }
+  mbar_wait(bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int n0 = 0; n0 < N; n0 += 8) {
+    float v[8];
+    TMEM_LD8(lane_base + 256 + n0, v);
+    for (int j = 0; j < 8; ++j) D[t * N + n0 + j] = v[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+int main() {
+  std::vector<float> hA(128 * 128), hW(128 * 128), hD(128 * 128);
+  uint32_t s = 777u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+  for (auto& x : hA) x = rnd() * 2.f;
+  for (auto& x : hW) x = rnd();
+  float *dA, *dW, *dD;
+  CK(cudaMalloc(&dA, 65536)); CK(cudaMalloc(&dW, 65536)); CK(cudaMalloc(&dD, 65536));
+  CK(cudaMemcpy(dA, hA.data(), 65536, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dW, hW.data(), 65536, cudaMemcpyHostToDevice));
+  const size_t smem = 12 * kPanel + 64 + 1024;
+  CK(cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int test = 1; test <= 2; ++test) {
+    std::vector<double> ref(128 * 128);
+    double scale = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 128; ++n) {
+        double acc = 0;
+        for (int k = 0; k < 128; ++k) {
+          const double a = test == 1 ? hA[m * 128 + k] : (double)hA[k * 128 + m];  // test 2: P[k][m]
+          acc += a * hW[k * 128 + n];
+        }
+        ref[m * 128 + n] = acc; scale = fmax(scale, fabs(acc));
+      }
+    CK(cudaMemset(dD, 0, 65536));
+    probe2<<<1, 128, smem>>>(dA, dW, dD, test);
+    CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(hD.data(), dD, 65536, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    for (int i = 0; i < 128 * 128; ++i) maxerr = fmax(maxerr, fabs(hD[i] - ref[i]));
+    printf("test %d (%s): max |err| = %.3e (max |ref| %.3f, rel %.3e)  D[0][1]=%.6f ref=%.6f  D[5][77]=%.6f ref=%.6f\n", test,
+           test == 1 ? "TS, B MN-major, 3xTF32" : "SS, A+B MN-major, P_hi only (expect ~1e-4 rel)", maxerr, scale, maxerr / scale, hD[1], ref[1], hD[5 * 128 + 77], ref[5 * 128 + 77]);
+  }
+  return 0;
+}
