@@ -79,6 +79,8 @@ struct marl_dqn {
   int32_t* idx = nullptr;
   uint8_t* image = nullptr;      // packed weight images for the tensor-core forward path (scratch, rebuilt per call)
   uint8_t* image_tgt = nullptr;  // image of theta_tgt, rebuilt only when the target network changed
+  uint8_t* image_bwd = nullptr;  // MN-major image of W2 (online net) for the tensor-core backward
+  float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh2 = nullptr, *tc_dh1 = nullptr, *tc_dq = nullptr;
   bool tgt_image_current = false;
   int64_t updates = 0, last_target_update = 0;
   RowPlan train_plan; int n_loss_parts = 0;
@@ -126,6 +128,7 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   if (rc) { marl_dqn_destroy(h); return MARL_ENOMEM; }
   if (int rc2 = learner_kernels_init(cfg->in_dim)) { marl_dqn_destroy(h); return rc2; }
   if (int rc2 = tc_forward_init()) { marl_dqn_destroy(h); return rc2; }
+  if (int rc2 = tc_train_init()) { marl_dqn_destroy(h); return rc2; }
   *out = h;
   return MARL_OK;
 }
@@ -134,7 +137,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
-  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh2); cudaFree(h->tc_dh1); cudaFree(h->tc_dq);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -205,7 +208,21 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   tp.gamma = h->hp.gamma; tp.double_q = h->hp.double_q; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch; tp.loss_part = loss_part;
   const bool rec = h->timing && h->ev_used < kTimingPairs;
   if (rec) cudaEventRecord(h->ev[2 * h->ev_used], st);
-  if (int rc = launch_train(tp, kHeadDqn, st)) return rc;
+  if (tc_backward_enabled() && h->ns.in < kMaxObsDim) {
+    if (!h->tc_h1) {  // intermediates of the tensor-core pipeline, allocated on first use
+      const size_t rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
+      int rc = 0;
+      rc |= dqn_alloc(&h->tc_h1, rows * kHidden); rc |= dqn_alloc(&h->tc_h2, rows * kHidden); rc |= dqn_alloc(&h->tc_dh2, rows * kHidden);
+      rc |= dqn_alloc(&h->tc_dh1, rows * kHidden); rc |= dqn_alloc(&h->tc_dq, rows * kOutPad);
+      rc |= dqn_alloc(reinterpret_cast<float**>(&h->image_bwd), (size_t)h->ns.n_nets * tc_bwd_image_bytes() / 4 + 4);
+      if (rc) return MARL_ENOMEM;
+    }
+    if (int rc = launch_pack_weights(h->theta, h->ns.lay, h->ns.n_nets, h->image, st, h->image_bwd)) return rc;
+    TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh2 = h->tc_dh2; tb.dh1 = h->tc_dh1; tb.dq = h->tc_dq;
+    if (int rc = launch_tc_dqn_train(tp, tb, st)) return rc;
+  } else {
+    if (int rc = launch_train(tp, kHeadDqn, st)) return rc;
+  }
   if (rec) { cudaEventRecord(h->ev[2 * h->ev_used + 1], st); h->ev_used += 1; }
   ReduceParams rp; rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->ns.n_nets; rp.P = h->ns.lay.P; rp.scratch_pitch = h->scratch_pitch;
   memcpy(rp.cta_begin, plan.cta_begin, sizeof(rp.cta_begin));

@@ -218,8 +218,16 @@ inline int launch_forward(const NetSet& ns, const RowPlan& plan, const RowSource
 // ---- tensor-core forward path (tc_forward.cu) -----------------------------------------------------------------------------
 size_t tc_image_bytes();
 int tc_forward_init();
-int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, uint8_t* image, cudaStream_t st);
+size_t tc_bwd_image_bytes();
+int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, uint8_t* image, cudaStream_t st, uint8_t* bwd_image = nullptr);
 int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st);
+// ---- tensor-core training pipeline (tc_train.cu) ----------------------------------------------------------------------------
+struct TcBuffers {
+  uint8_t* image; uint8_t* bwd_image;       // packed online-network images (forward K-major, backward MN-major W2)
+  float *h1, *h2, *dh2, *dh1, *dq;          // [rows][128] x4 and [rows][8] intermediates
+};
+int tc_train_init();
+int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_t st);
 // tc_forward_enabled(): process-wide switch (marl_set_option("tensor_core_forward", 0|1)), declared in common.cuh
 
 // Forward pass through whichever implementation is selected.  `image` is scratch for the packed weights (n_nets images);

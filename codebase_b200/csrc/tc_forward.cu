@@ -12,29 +12,12 @@
 //     accumulator (measured 4e-7 relative on a 128x128x128 product, tools/tc_probe.cu).
 // One elected thread issues tcgen05.mma (kind::tf32, cta_group::1, M = 128, N = 128 or 16); completion reaches the
 // other threads through tcgen05.commit -> mbarrier.
-#include "learner.cuh"
+#include "tc_common.cuh"
 
 namespace marl {
 
-constexpr int kTcThreads = 128;
-constexpr int kPanelBytes = kHidden * 128;         // 128 rows x 32 floats
-constexpr int kHeadRows = 16;                      // head GEMM uses N = 16 (minimum for M = 128)
-constexpr int kHeadPanelBytes = kHeadRows * 128;
-// image layout (bytes): W1 hi | W1 lo | W2 hi (4 panels) | W2 lo | W3 hi (4 panels of 16 rows) | W3 lo | b1 | b2 | b3
-constexpr int kOffW1Hi = 0, kOffW1Lo = kOffW1Hi + kPanelBytes, kOffW2Hi = kOffW1Lo + kPanelBytes, kOffW2Lo = kOffW2Hi + 4 * kPanelBytes;
-constexpr int kOffW3Hi = kOffW2Lo + 4 * kPanelBytes, kOffW3Lo = kOffW3Hi + 4 * kHeadPanelBytes;
-constexpr int kOffB1 = kOffW3Lo + 4 * kHeadPanelBytes, kOffB2 = kOffB1 + kHidden * 4, kOffB3 = kOffB2 + kHidden * 4;
-constexpr int kImageBytes = kOffB3 + kHeadRows * 4;
-constexpr int kTcSmemBytes = kImageBytes + 64 + 1024;  // + mbarrier / TMEM slot, + slack for 1024-byte alignment
-
 size_t tc_image_bytes() { return kImageBytes; }
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+size_t tc_bwd_image_bytes() { return kBwdImageBytes; }
 
 // ---- weight image --------------------------------------------------------------------------------------------------
 // element (row n, feature k) of a [rows][K] K-major operand -> byte offset inside its panel set
@@ -43,7 +26,7 @@ __device__ __forceinline__ int panel_offset(int n, int k, int panel_bytes) {
   return p * panel_bytes + n * 128 + ((c ^ (n & 7)) << 4) + (w << 2);
 }
 
-__global__ void pack_weights_kernel(const float* __restrict__ theta, NetLayout lay, int n_nets, uint8_t* __restrict__ image) {
+__global__ void pack_weights_kernel(const float* __restrict__ theta, NetLayout lay, int n_nets, uint8_t* __restrict__ image, uint8_t* __restrict__ bwd_image) {
   const int net = blockIdx.y;
   if (net >= n_nets) return;
   const float* th = theta + (size_t)net * lay.P;
@@ -73,85 +56,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ theta, NetLayout l
     reinterpret_cast<float*>(img + kOffB2)[i] = th[lay.b2 + i];
   }
   if (i < kHeadRows) reinterpret_cast<float*>(img + kOffB3)[i] = i < lay.out ? th[lay.b3 + i] : 0.f;
+  if (i < kOutPad * kHidden) reinterpret_cast<float*>(img + kOffW3F)[i] = (i >> 7) < lay.out ? th[lay.w3 + i] : 0.f;
+  if (bwd_image != nullptr && i < kHidden * kHidden) {  // W2[k = j2][n = j1], MN-major BASE32B, hi | lo
+    const int k = i >> 7, n = i & 127;
+    const float x = th[lay.w2 + i], hi = tf32_rn(x);
+    uint8_t* bi = bwd_image + (size_t)net * kBwdImageBytes;
+    *reinterpret_cast<float*>(bi + mn_offset(k, n, kPanelBytes)) = hi;
+    *reinterpret_cast<float*>(bi + 4 * kPanelBytes + mn_offset(k, n, kPanelBytes)) = tf32_rn(x - hi);
+  }
 }
 
-// ---- tcgen05 helpers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4, LBO 1, SBO 1024 B,
-// version 1, layout type 2
-__device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128
-__device__ __forceinline__ uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
-
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(addr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
-                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// issue only; the caller waits with tmem_ld_wait() before touching r[]
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(addr));
-}
-// the registers are in/out operands of the wait so that no use of them can be scheduled ahead of it
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
-                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
-               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
-               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
-               "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
-               "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-               : "memory");
-}
-
-// TMEM columns: A hi [0,128), A lo [128,256), D [256,384), head D [384,400)
-constexpr uint32_t kColAHi = 0, kColALo = 128, kColD = 256, kColDHead = 384;
 
 // 3xTF32: D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over KSTEPS steps of 8 features; issued by one thread.
 // Fully unrolled: every operand address is base + compile-time constant (the descriptor's address field counts
@@ -313,9 +227,9 @@ int tc_forward_init() {
   return MARL_OK;
 }
 
-int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, uint8_t* image, cudaStream_t st) {
+int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, uint8_t* image, cudaStream_t st, uint8_t* bwd_image) {
   dim3 grid((kHidden * kHidden + 255) / 256, n_nets);
-  pack_weights_kernel<<<grid, 256, 0, st>>>(theta, lay, n_nets, image);
+  pack_weights_kernel<<<grid, 256, 0, st>>>(theta, lay, n_nets, image, bwd_image);
   MARL_CUDA_TRY(cudaGetLastError());
   return MARL_OK;
 }

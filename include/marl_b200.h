@@ -32,7 +32,8 @@ extern "C" {
 
 int marl_version(void);
 const char* marl_last_error(void);
-/* Process-wide options: "tensor_core_forward" 1 (default) = forward-only passes on tcgen05 with the 3xTF32 split, 0 = FP32 FFMA. */
+/* Process-wide options: "tensor_core_forward" 1 (default) = forward-only passes on tcgen05 with the 3xTF32 split, 0 = FP32 FFMA;
+ * "tensor_core_backward" 1 = the DQN-family training pass runs as the three-kernel tcgen05 pipeline (tc_train.cu), 0 = fused FP32 kernel. */
 int marl_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------------
