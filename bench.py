@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tc-backward", type=int, default=1, help="1 = three-kernel tcgen05 training pipeline (default), 0 = fused FP32 FFMA training kernel")
     return ap.parse_args()
 
 
@@ -159,6 +160,7 @@ def run_b200(args):
     rb = TrajStore(args.buffer, env.n_agents, T, env.cfg.obs_dim, dev)
     coll = Collector(env, model, T)
     lib = nat.lib()
+    nat.check(lib.marl_set_option(b"tensor_core_backward", C.c_int32(int(args.tc_backward))), "marl_set_option")
     state = dict(pos=0, updates=0)
     steps_dev = torch.zeros((), dtype=torch.int64, device=dev)
     # pinned host mirrors for the e2e leg

@@ -213,7 +213,7 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
       const size_t rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
       int rc = 0;
       rc |= dqn_alloc(&h->tc_h1, rows * kHidden); rc |= dqn_alloc(&h->tc_h2, rows * kHidden); rc |= dqn_alloc(&h->tc_dh2, rows * kHidden);
-      rc |= dqn_alloc(&h->tc_dh1, rows * kHidden); rc |= dqn_alloc(&h->tc_dq, rows * kOutPad);
+      rc |= dqn_alloc(&h->tc_dh1, rows * kHidden); rc |= dqn_alloc(&h->tc_dq, rows * 16 /* kRowRec */);
       rc |= dqn_alloc(reinterpret_cast<float**>(&h->image_bwd), (size_t)h->ns.n_nets * tc_bwd_image_bytes() / 4 + 4);
       if (rc) return MARL_ENOMEM;
     }

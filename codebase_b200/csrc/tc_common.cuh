@@ -24,11 +24,12 @@ constexpr int kTcSmemBytes = kImageBytes + 64 + 1024;
 constexpr uint32_t kColAHi = 0, kColALo = 128, kColD = 256, kColDHead = 384;  // + mbarrier / TMEM slot, + slack for 1024-byte alignment
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+// round to TF32 (10-bit mantissa), nearest with ties away from zero: what cvt.rna.tf32.f32 computes for finite inputs, in two
+// integer instructions instead of the five the compiler emits for the cvt (its extra work is NaN / infinity handling)
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// dynamic shared memory rounded up to 1024 bytes (swizzle atoms), keeping the pointer in the shared address space so that the
+// compiler emits LDS / STS rather than generic loads and stores
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) { return raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(raw) & 1023u)) & 1023u); }
 
 // ---- tcgen05 helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -121,6 +122,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
                "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
                : "memory");
 }
-
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 
 }  // namespace marl

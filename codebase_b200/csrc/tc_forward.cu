@@ -91,7 +91,7 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t d_col, uint3
 
 __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, const uint8_t* __restrict__ images) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms need 1024-byte alignment
+  uint8_t* smem = align_smem_1024(smem_raw);  // swizzle atoms need 1024-byte alignment
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kImageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int t = threadIdx.x, warp = t >> 5;

@@ -36,7 +36,7 @@ def test_dense_forward_tc_vs_ffma_vs_oracle(n_agents, D, sharing, E):
     cfg = types.SimpleNamespace(optimizer="Adam", lr=3e-4, gamma=0.99, grad_clip=1.0, double_q=True, target_update_interval_or_tau=200, standardise_returns=False)
     m = QNetwork([_space(shape=(D,))] * n_agents, [_space(n=6)] * n_agents, cfg, [128, 128], sharing, False, True, "cuda", max_batch=8, max_episode_length=25)
     m.theta.mul_(1.7)  # not the orthogonal-init special case
-    m.theta.add_(0.01 * torch.randn_like(m.theta))
+    m.theta.add_(torch.as_tensor(0.01 * rng.standard_normal(m.theta.numel()), dtype=torch.float32).to(m.theta.device).view_as(m.theta))
     obs = torch.tensor(rng.integers(-1, 15, size=(E, n_agents, D)).astype(np.float32), device="cuda")
     _set_tc(True)
     q_tc = m.q_values(obs).cpu().numpy()
