@@ -218,7 +218,7 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
       if (rc) return MARL_ENOMEM;
     }
     if (int rc = launch_pack_weights(h->theta, h->ns.lay, h->ns.n_nets, h->image, st, h->image_bwd)) return rc;
-    TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh2 = h->tc_dh2; tb.dh1 = h->tc_dh1; tb.dq = h->tc_dq;
+    TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh2 = h->tc_dh2; tb.dh1 = h->tc_dh1; tb.dq = h->tc_dq; tb.rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
     if (int rc = launch_tc_dqn_train(tp, tb, st)) return rc;
   } else {
     if (int rc = launch_train(tp, kHeadDqn, st)) return rc;

@@ -224,7 +224,8 @@ int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st
 // ---- tensor-core training pipeline (tc_train.cu) ----------------------------------------------------------------------------
 struct TcBuffers {
   uint8_t* image; uint8_t* bwd_image;       // packed online-network images (forward K-major, backward MN-major W2)
-  float *h1, *h2, *dh2, *dh1, *dq;          // [rows][128] x4 and [rows][8] intermediates
+  float *h1, *h2, *dh2, *dh1, *dq;          // [32][rows][4] x4 (chunk-major) and [rows][16] row records
+  size_t rows;                               // allocated rows
 };
 int tc_train_init();
 int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_t st);

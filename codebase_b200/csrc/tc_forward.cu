@@ -89,12 +89,14 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t d_col, uint3
   }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, const uint8_t* __restrict__ images) {
+// 16 warps: warp w owns TMEM lane quarter (w & 3) -- rows 32 (w & 3) .. +31 of the tile -- and column quarter (w >> 2) of the
+// 128 hidden features, so that four warps per SM sub-partition overlap their TMEM / shared / global latencies.
+__global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, const uint8_t* __restrict__ images) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);  // swizzle atoms need 1024-byte alignment
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kImageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x, warp = t >> 5, lq = warp & 3, cq = warp >> 2, r = 32 * lq + (t & 31), c0 = 32 * cq;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   if (row_begin >= row_end) return;
@@ -104,57 +106,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) mbar_init(bar, 1);
-  {  // the weight image is already in shared-memory layout: asynchronous 16-byte copies, all in flight at once
+  {  // the weight image is already in shared-memory layout: asynchronous 16-byte copies in three groups, in the order the first
+     // tile needs them (W1 + biases, W2, W3), so that its first layer does not wait for the whole image
     const uint8_t* src = images + (size_t)net * kImageBytes;
     const uint32_t dst = smem_u32(smem);
-#pragma unroll 4
-    for (int i = t; i < kImageBytes / 16; i += kTcThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    auto copy = [&](int begin, int end) {
+      for (int i = begin / 16 + t; i < end / 16; i += kTrThreads)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
+    };
+    copy(kOffW1Hi, kOffW2Hi); copy(kOffB1, kImageBytes);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    copy(kOffW2Hi, kOffW3Hi);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    copy(kOffW3Hi, kOffB1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_base = tmem + ((uint32_t)(32 * lq) << 16);
   const float* b1 = reinterpret_cast<const float*>(smem + kOffB1);
   const float* b2 = reinterpret_cast<const float*>(smem + kOffB2);
   const float* b3 = reinterpret_cast<const float*>(smem + kOffB3);
   const int D = p.src.D, out = p.lay.out;
   const int k1steps = (D + 7) >> 3;
+  const bool x_active = cq < k1steps;   // column quarter cq stages observation columns [8 cq, 8 cq + 8)
+  int image_groups_pending = 3;         // block-uniform
   uint32_t parity = 0;
-  // this thread's input row of the current tile (prefetched one tile ahead) and where its outputs go
-  float xin[kMaxObsDim];
+  // this thread's 8 observation columns of its row (prefetched one tile ahead) and where the row's outputs go
+  float xin[8], xnext[8];
   size_t dst_row = 0, dst_next = 0;
-  auto fetch_row = [&](int vr0, int nrows, size_t& dst) {
-    const float* src = nullptr;
-    if (t < nrows) {
-      int agent, unit, off;
-      decode_row(p.plan, net, vr0 + t, agent, unit, off);
-      src = row_ptr(p.src, agent, unit, off);
-      dst = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent) : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
-    }
+  auto fetch_row = [&](int vr0, int nrows, size_t& dst, float (&x)[8]) {
 #pragma unroll
-    for (int j = 0; j < kMaxObsDim; ++j) xin[j] = (src != nullptr && j < D) ? src[j] : 0.f;
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    if (r < nrows) {
+      int agent, unit, off;
+      decode_row(p.plan, net, vr0 + r, agent, unit, off);
+      const float* src = row_ptr(p.src, agent, unit, off);
+      dst = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent) : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
+      if (x_active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (8 * cq + j < D) ? src[8 * cq + j] : 0.f;
+      }
+    }
   };
-  fetch_row(row_begin, min(kTileRows, row_end - row_begin), dst_row);
+  fetch_row(row_begin, min(kTileRows, row_end - row_begin), dst_row, xin);
 
   for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
     const int nrows = min(kTileRows, row_end - vr0);
     // ---- input row -> A operand (hi / lo), zero padded to k1steps * 8 features -----------------------------------
+    if (x_active) {
+      float hi[8], lo[8];
 #pragma unroll
-    for (int k0 = 0; k0 < kMaxObsDim; k0 += 16) {
-      if (k0 < k1steps * 8) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { hi[j] = tf32_rn(xin[k0 + j]); lo[j] = tf32_rn(xin[k0 + j] - hi[j]); }
-        tmem_st16(lane_base + kColAHi + k0, hi);
-        tmem_st16(lane_base + kColALo + k0, lo);
-      }
+      for (int j = 0; j < 8; ++j) { hi[j] = tf32_rn(xin[j]); lo[j] = tf32_rn(xin[j] - hi[j]); }
+      tmem_st8(lane_base + kColAHi + 8 * cq, hi);
+      tmem_st8(lane_base + kColALo + 8 * cq, lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (image_groups_pending == 3) { asm volatile("cp.async.wait_group 2;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); image_groups_pending = 2; }
     tc_fence_before();
     __syncthreads();
     // ---- layer 1 -------------------------------------------------------------------------------------------------
@@ -164,33 +175,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
       mma_commit(bar);
     }
     // prefetch the next tile's rows: the loads stay in flight under this tile's epilogues and MMAs
-    if (vr0 + kTileRows < row_end) fetch_row(vr0 + kTileRows, min(kTileRows, row_end - vr0 - kTileRows), dst_next);
+    if (vr0 + kTileRows < row_end) fetch_row(vr0 + kTileRows, min(kTileRows, row_end - vr0 - kTileRows), dst_next, xnext);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
-    // ---- bias + ReLU, next A operand (twice: after layer 1 and after layer 2) ------------------------------------------
+    // ---- bias + ReLU, next A operand (twice: after layer 1 and after layer 2): this thread's 32 columns --------------------
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
-      const float* bias = layer == 0 ? b1 : b2;
-      // software pipeline over 16-column chunks: the TMEM load of chunk c+1 is in flight while chunk c is processed
+      const float* bias = (layer == 0 ? b1 : b2) + c0;
       uint32_t ra[16], rb[16];
-      tmem_ld16_issue(lane_base + kColD, ra);
+      tmem_ld16_issue(lane_base + kColD + c0, ra);
+      tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
       tmem_ld_wait(ra);
+      tmem_ld_wait(rb);
 #pragma unroll
-      for (int c = 0; c < kHidden / 16; ++c) {
-        uint32_t (&cur)[16] = (c & 1) ? rb : ra;
-        uint32_t (&nxt)[16] = (c & 1) ? ra : rb;
-        if (c + 1 < kHidden / 16) tmem_ld16_issue(lane_base + kColD + 16 * (c + 1), nxt);
+      for (int half = 0; half < 2; ++half) {
+        uint32_t (&acc)[16] = half ? rb : ra;
         float hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float h = fmaxf(__uint_as_float(cur[j]) + bias[16 * c + j], 0.f);
+          const float h = fmaxf(__uint_as_float(acc[j]) + bias[16 * half + j], 0.f);
           hi[j] = tf32_rn(h); lo[j] = tf32_rn(h - hi[j]);
         }
-        tmem_st16(lane_base + kColAHi + 16 * c, hi);
-        tmem_st16(lane_base + kColALo + 16 * c, lo);
-        if (c + 1 < kHidden / 16) tmem_ld_wait(nxt);
+        tmem_st16(lane_base + kColAHi + c0 + 16 * half, hi);
+        tmem_st16(lane_base + kColALo + c0 + 16 * half, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      if (image_groups_pending == 2 - layer) {   // W2 before the layer-2 MMAs, W3 before the head's
+        if (layer == 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        image_groups_pending = 1 - layer;
+      }
       tc_fence_before();
       __syncthreads();
       if (t == 0) {
@@ -202,19 +216,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(FwdParams p, 
       mbar_wait(bar, parity); parity ^= 1;
       tc_fence_after();
     }
-    // ---- head epilogue: outputs to global -------------------------------------------------------------------------------
-    {
+    // ---- head epilogue: outputs to global (column quarter 0) ---------------------------------------------------------------
+    if (cq == 0) {
       float v[16];
       tmem_ld16(lane_base + kColDHead, v);
-      if (t < nrows) {
+      if (r < nrows) {
         float* dst = p.out + dst_row * out;
-        for (int o = 0; o < out; ++o) dst[o] = v[o] + b3[o];
+#pragma unroll
+        for (int o = 0; o < kOutPad; ++o) if (o < out) dst[o] = v[o] + b3[o];
       }
     }
     dst_row = dst_next;
-    tc_fence_before();
-    __syncthreads();  // every lane has consumed D before the next tile's MMAs overwrite it
-    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xin[j] = xnext[j];
+    // the next tile's first MMAs write D / read A only after the __syncthreads that follows its operand staging, by which time
+    // every warp has finished reading this tile's accumulators
   }
   tc_fence_before();
   __syncthreads();
@@ -235,7 +251,7 @@ int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, ui
 }
 
 int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st) {
-  tc_forward_kernel<<<p.plan.cta_begin[p.plan.n_nets], kTcThreads, kTcSmemBytes, st>>>(p, images);
+  tc_forward_kernel<<<p.plan.cta_begin[p.plan.n_nets], kTrThreads, kTcSmemBytes, st>>>(p, images);
   MARL_CUDA_TRY(cudaGetLastError());
   return MARL_OK;
 }

@@ -19,10 +19,13 @@ struct TcTrainParams {
   const uint8_t* images;      // forward images [n_nets][kImageBytes]
   const uint8_t* bwd_images;  // backward images [n_nets][kBwdImageBytes]
   float* q_out;               // [rows][out] online outputs (optional)
-  float* h1g; float* h2g; float* dh2g; float* dh1g;  // [rows][128] x4
+  // H1, H2, dH2, dH1: [32 float4 column chunks][rows][4] -- chunk-major, so that a warp whose lanes are 32 consecutive rows writes or
+  // reads 512 contiguous bytes per instruction (row-major rows of 512 B cost one cache line per lane and instruction)
+  float* h1g; float* h2g; float* dh2g; float* dh1g; size_t rows;
   float* dqg;  // [rows][kRowRec] row records: dq[8] | ReLU mask of H1 (4 words) | observation offset (int64) | pad
   const float* tq; const float* td_ext; float gamma; int double_q;
   float* scratch; int scratch_pitch; float* loss_part;
+  int debug;
 };
 
 __device__ __forceinline__ size_t dst_of(const RowPlan& plan, const RowSource& src, int net, int vr, int& agent, int& unit, int& off) {
@@ -61,7 +64,6 @@ __device__ __forceinline__ void issue_kmajor(uint32_t tmem, uint32_t d_col, uint
 // lanes 32 (w % 4) .. +31) and on column quarter cq = w >> 2 of the 128 hidden features, so every SM sub-partition holds four
 // warps whose TMEM / global latencies overlap (with one warp per sub-partition the kernels sat at 15 % issue utilisation).
 // =====================================================================================================================
-constexpr int kTrThreads = 512;
 
 __device__ __forceinline__ void split16(const float (&h)[16], float (&hi)[16], float (&lo)[16]) {
 #pragma unroll
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     __syncthreads();
     if (t == 0) {
       tc_fence_after();
-      issue_kmajor<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
+      if (!(p.debug & 4)) issue_kmajor<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
       mma_commit(bar);
     }
     const size_t dst_row = cur.dst;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
       const float* bias = (layer == 0 ? b1 : b2) + c0;
-      float* hg = (layer == 0 ? p.h1g : p.h2g) + dst_row * kHidden + c0;
+      float4* hg = reinterpret_cast<float4*>(layer == 0 ? p.h1g : p.h2g) + dst_row;
       uint32_t ra[16], rb[16];
       tmem_ld16_issue(lane_base + kColD + c0, ra);
       tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
@@ -200,7 +202,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
         split16(h, hi, lo);
         tmem_st16(lane_base + kColAHi + c0 + 16 * half, hi);
         tmem_st16(lane_base + kColALo + c0 + 16 * half, lo);
-        if (r < nrows) store16(hg + 16 * half, h);
+        if (r < nrows && !(p.debug & 1)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hg[(size_t)(8 * cq + 4 * half + j) * p.rows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+        }
       }
       h2mask = mask;
       if (image_groups_pending == 2 - layer) {   // W2 before the layer-2 MMAs, W3 before the head's
@@ -214,7 +219,8 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
       __syncthreads();
       if (t == 0) {
         tc_fence_after();
-        if (layer == 0) issue_kmajor<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
+        if (p.debug & 4) {}
+        else if (layer == 0) issue_kmajor<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
         else issue_kmajor<kHidden / 8, kHeadRows, kHeadPanelBytes>(tmem, kColDHead, smem_base + kOffW3Hi, smem_base + kOffW3Lo, kHidden / 8);
         mma_commit(bar);
       }
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     __syncthreads();
     if (cq == 0) {
       float g = 0.f;
-      if (r < nrows) {
+      if (r < nrows && !(p.debug & 8)) {
         if (p.q_out) for (int o = 0; o < A; ++o) p.q_out[dst_row * A + o] = q[o];
         if (tt < T) {
           if (p.td_ext) {
@@ -278,10 +284,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
       for (int o = 0; o < kOutPad; ++o) carry[o] = q[o];
     }
     // ---- dH2[r][j] = dq[r][act] W3[act][j] (H2[r][j] > 0): dq has one non-zero per row, the ReLU mask is still in registers ----
-    if (r < nrows) {
+    if (r < nrows && !(p.debug & 2)) {
       const float g = gsm[r];
       const float4* wrow = reinterpret_cast<const float4*>(w3f + actsm[r] * kHidden + c0);
-      float4* dst = reinterpret_cast<float4*>(p.dh2g + dst_row * kHidden + c0);
+      float4* dst = reinterpret_cast<float4*>(p.dh2g) + dst_row;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const float4 w = wrow[jj];
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
         d.y = (h2mask >> (4 * jj + 1)) & 1u ? g * w.y : 0.f;
         d.z = (h2mask >> (4 * jj + 2)) & 1u ? g * w.z : 0.f;
         d.w = (h2mask >> (4 * jj + 3)) & 1u ? g * w.w : 0.f;
-        dst[jj] = d;
+        dst[(size_t)(8 * cq + jj) * p.rows] = d;
       }
     }
     cur = nxt;
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
   };
   auto load8 = [&](const float* base, long long d, float4 (&v)[8]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = d >= 0 ? reinterpret_cast<const float4*>(base + d * kHidden + c0)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 8; ++j) v[j] = d >= 0 ? reinterpret_cast<const float4*>(base)[(size_t)(8 * cq + j) * p.rows + d] : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   long long d_cur = row_of(row_begin), d_nxt = -1;
   float4 in_cur[8], in_nxt[8];
@@ -373,12 +379,14 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
     if (t == 0) {
       tc_fence_after();
       // D[r][j1] = sum_{j2} dH2[r][j2] W2[j2][j1]: k-step = 8 rows of the [k = j2][n = j1] image (1024 bytes), panels 16 KB apart
+      if (!(p.debug & 64)) {
 #pragma unroll
       for (int term = 0; term < 3; ++term)
 #pragma unroll
         for (int ks = 0; ks < kHidden / 8; ++ks)
           mma_tf32_ts(tmem + kColD, tmem + (term == 0 ? kColALo : kColAHi) + ks * 8,
                       mnmajor_desc(smem_base + (term == 1 ? 4 * kPanelBytes : 0) + ks * 1024, kPanelBytes), idesc, (term | ks) ? 1u : 0u);
+      }
       mma_commit(bar);
     }
     // H1's ReLU mask (one word per thread, written by tc_dqn_fwd_kernel) and the next tile's dH2 are fetched while the MMAs run
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
       tmem_ld_wait(ra);
       tmem_ld_wait(rb);
       if (d_cur >= 0) {
-        float4* gout = reinterpret_cast<float4*>(p.dh1g + d_cur * kHidden + c0);
+        float4* gout = reinterpret_cast<float4*>(p.dh1g) + d_cur;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t (&acc)[16] = j < 4 ? ra : rb;
@@ -401,7 +409,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
           float4 d;
           d.x = (m1 >> (4 * j)) & 1u ? __uint_as_float(acc[o]) : 0.f; d.y = (m1 >> (4 * j + 1)) & 1u ? __uint_as_float(acc[o + 1]) : 0.f;
           d.z = (m1 >> (4 * j + 2)) & 1u ? __uint_as_float(acc[o + 2]) : 0.f; d.w = (m1 >> (4 * j + 3)) & 1u ? __uint_as_float(acc[o + 3]) : 0.f;
-          gout[j] = d;
+          gout[(size_t)(8 * cq + j) * p.rows] = d;
         }
       }
     }
@@ -443,7 +451,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSEnd);   // [0], [1]: chunk buffer consumed; [2]: everything done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  const int t = threadIdx.x, warp = t >> 5, rr = t >> 5, c4 = t & 31;   // staging: chunk row rr (one warp per row), float4 column c4
+  // staging: warp = (4-row group, 32-feature panel), lane = (float4 column within the panel, row within the group): shared-memory
+  // stores of the swizzled MN-major image stay conflict-free and every global load instruction reads eight 64-byte segments
+  const int t = threadIdx.x, warp = t >> 5, rr = 4 * (warp >> 2) + (t & 3), c4 = 8 * (warp & 3) + ((t & 31) >> 2);
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   float* gs = p.scratch + (size_t)blockIdx.x * p.scratch_pitch;
@@ -480,16 +490,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
       else { const int slot = vr / rpa; d = (size_t)p.plan.slot_agent[p.plan.slot_begin[net] + slot] * rpa + (vr - slot * rpa); }  // dst_of(), one division
       const float* rec = p.dqg + d * kRowRec;
       const float* xp = obs_base + *reinterpret_cast<const long long*>(rec + 12);
-      pre.v[0] = reinterpret_cast<const float4*>(p.dh2g + d * kHidden)[c4];
-      pre.v[1] = reinterpret_cast<const float4*>(p.h1g + d * kHidden)[c4];
-      pre.v[2] = reinterpret_cast<const float4*>(p.dh1g + d * kHidden)[c4];
-      pre.v[3] = reinterpret_cast<const float4*>(p.h2g + d * kHidden)[c4];
+      const size_t hi = (size_t)c4 * p.rows + d;
+      pre.v[0] = reinterpret_cast<const float4*>(p.dh2g)[hi];
+      pre.v[1] = reinterpret_cast<const float4*>(p.h1g)[hi];
+      pre.v[2] = reinterpret_cast<const float4*>(p.dh1g)[hi];
+      pre.v[3] = reinterpret_cast<const float4*>(p.h2g)[hi];
       pre.xv = c4 < D ? xp[c4] : (c4 == D ? 1.f : 0.f);   // [X | 1]: the ones column carries db1
       if (c4 < kOutPad) pre.gv = rec[c4];
     }
   };
   float db3 = 0.f;  // this thread's share of sum_r dq[r][c4]
   auto stage = [&](uint8_t* bufp, const Pre& pre) {
+    if (p.debug & 32) { db3 += pre.v[0].x + pre.v[1].x + pre.v[2].x + pre.v[3].x + pre.xv + pre.gv; return; }
     stage4(bufp + kSDh2, bufp + kSDh2 + kOpBytes, rr, 4 * c4, pre.v[0]);
     stage4(bufp + kSH1, bufp + kSH1 + kOpBytes + kChunkPanel, rr, 4 * c4, pre.v[1]);
     stage4(bufp + kSDh1, bufp + kSDh1 + kOpBytes, rr, 4 * c4, pre.v[2]);
@@ -512,6 +524,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   // one thread: the 18 MMAs of a chunk (3xTF32 terms x 2 k-steps x 3 GEMMs), then a commit onto the buffer's barrier
   auto issue_mmas = [&](uint32_t base, bool first, uint64_t* bar) {
     tc_fence_after();
+    if (p.debug & 16) { mma_commit(bar); return; }
 #pragma unroll
     for (int term = 0; term < 3; ++term) {
       const uint32_t a_sel = term == 0 ? 1u : 0u, b_sel = term == 1 ? 1u : 0u;  // lo*hi, hi*lo, hi*hi
@@ -558,16 +571,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   // db3[a] = sum over the threads whose panel column c4 is a
   __syncthreads();
   float* red = reinterpret_cast<float*>(smem);  // operands are dead
-  red[t] = db3;
+  if (t < kOutPad) red[t] = 0.f;
   __syncthreads();
-  if (t < A) {
-    float s = 0.f;
-    for (int w = 0; w < kDwThreads / 32; ++w) s += red[w * 32 + t];
-    gs[p.lay.b3 + t] = s;
-  }
+  if (c4 < kOutPad) atomicAdd(red + c4, db3);   // 64 threads hold partial sums of the 8 dq columns
+  __syncthreads();
+  if (t < A) gs[p.lay.b3 + t] = red[t];
   // ---- flush: lane j of lane quarter lq owns output feature j; the column quarters share its accumulator columns -----------
   {
-    const int lq = warp & 3, cq = warp >> 2, j = 32 * lq + c4;
+    const int lq = warp & 3, cq = warp >> 2, j = 32 * lq + (t & 31);
     const uint32_t lane_base = tmem + ((uint32_t)(32 * lq) << 16);
     float v[16];
 #pragma unroll
@@ -617,9 +628,9 @@ int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_
   MARL_REQUIRE(tp.lay.in < kMaxObsDim, "tensor-core backward: observation width %d needs a spare column for the bias trick (max %d)", tp.lay.in, kMaxObsDim - 1);
   TcTrainParams p; memset(&p, 0, sizeof(p));
   p.plan = tp.plan; p.src = tp.src; p.lay = tp.lay; p.images = buf.image; p.bwd_images = buf.bwd_image; p.q_out = nullptr;
-  p.h1g = buf.h1; p.h2g = buf.h2; p.dh2g = buf.dh2; p.dh1g = buf.dh1; p.dqg = buf.dq;
+  p.h1g = buf.h1; p.h2g = buf.h2; p.dh2g = buf.dh2; p.dh1g = buf.dh1; p.dqg = buf.dq; p.rows = buf.rows;
   p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
-  p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
+  p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part; p.debug = tc_debug_bits();
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
   tc_dqn_fwd_kernel<<<grid, kTrThreads, kFwdTrainSmem, st>>>(p);
   MARL_CUDA_TRY(cudaGetLastError());
