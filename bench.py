@@ -161,8 +161,6 @@ def run_b200(args):
     coll = Collector(env, model, T)
     lib = nat.lib()
     nat.check(lib.marl_set_option(b"tensor_core_backward", C.c_int32(int(args.tc_backward))), "marl_set_option")
-    if os.environ.get("MARL_TC_DEBUG"):
-        lib.marl_set_option(b"tc_debug", C.c_int32(int(os.environ["MARL_TC_DEBUG"])))
     state = dict(pos=0, updates=0)
     steps_dev = torch.zeros((), dtype=torch.int64, device=dev)
     # pinned host mirrors for the e2e leg

@@ -74,6 +74,5 @@ __host__ __device__ __forceinline__ float u01(uint32_t u) { return (float)(u >> 
 int check_device(int device);
 int tc_forward_enabled();
 int tc_backward_enabled();
-int tc_debug_bits();  // TEMPORARY phase knock-out bits for profiling experiments
 
 }  // namespace marl

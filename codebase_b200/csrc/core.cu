@@ -32,10 +32,9 @@ int check_device(int device) {
   return MARL_OK;
 }
 
-static int g_tc_forward = 1, g_tc_backward = 0, g_tc_debug = 0;
+static int g_tc_forward = 1, g_tc_backward = 0;
 int tc_forward_enabled() { return g_tc_forward; }
 int tc_backward_enabled() { return g_tc_backward; }
-int tc_debug_bits() { return g_tc_debug; }
 
 }  // namespace marl
 
@@ -44,7 +43,6 @@ extern "C" {
  * 3xTF32 split (default), 0 = FP32 FFMA kernels. */
 int marl_set_option(const char* name, int32_t value) {
   if (name && strcmp(name, "tensor_core_forward") == 0) { marl::g_tc_forward = value ? 1 : 0; return MARL_OK; }
-  if (name && strcmp(name, "tc_debug") == 0) { marl::g_tc_debug = value; return MARL_OK; }
   if (name && strcmp(name, "tensor_core_backward") == 0) { marl::g_tc_backward = value ? 1 : 0; return MARL_OK; }
   marl::set_error("marl_set_option: unknown option '%s'", name ? name : "(null)");
   return MARL_EINVAL;

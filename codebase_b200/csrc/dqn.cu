@@ -80,7 +80,7 @@ struct marl_dqn {
   uint8_t* image = nullptr;      // packed weight images for the tensor-core forward path (scratch, rebuilt per call)
   uint8_t* image_tgt = nullptr;  // image of theta_tgt, rebuilt only when the target network changed
   uint8_t* image_bwd = nullptr;  // MN-major image of W2 (online net) for the tensor-core backward
-  float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh2 = nullptr, *tc_dh1 = nullptr, *tc_dq = nullptr;
+  float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh1 = nullptr, *tc_rec = nullptr;
   bool tgt_image_current = false;
   int64_t updates = 0, last_target_update = 0;
   RowPlan train_plan; int n_loss_parts = 0;
@@ -137,7 +137,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
-  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh2); cudaFree(h->tc_dh1); cudaFree(h->tc_dq);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -212,13 +212,13 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
     if (!h->tc_h1) {  // intermediates of the tensor-core pipeline, allocated on first use
       const size_t rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
       int rc = 0;
-      rc |= dqn_alloc(&h->tc_h1, rows * kHidden); rc |= dqn_alloc(&h->tc_h2, rows * kHidden); rc |= dqn_alloc(&h->tc_dh2, rows * kHidden);
-      rc |= dqn_alloc(&h->tc_dh1, rows * kHidden); rc |= dqn_alloc(&h->tc_dq, rows * 16 /* kRowRec */);
+      rc |= dqn_alloc(&h->tc_h1, rows * kHidden); rc |= dqn_alloc(&h->tc_h2, rows * kHidden);
+      rc |= dqn_alloc(&h->tc_dh1, rows * kHidden); rc |= dqn_alloc(&h->tc_rec, rows * 16 /* kRowRec */);
       rc |= dqn_alloc(reinterpret_cast<float**>(&h->image_bwd), (size_t)h->ns.n_nets * tc_bwd_image_bytes() / 4 + 4);
       if (rc) return MARL_ENOMEM;
     }
     if (int rc = launch_pack_weights(h->theta, h->ns.lay, h->ns.n_nets, h->image, st, h->image_bwd)) return rc;
-    TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh2 = h->tc_dh2; tb.dh1 = h->tc_dh1; tb.dq = h->tc_dq; tb.rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
+    TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh1 = h->tc_dh1; tb.rec = h->tc_rec; tb.rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
     if (int rc = launch_tc_dqn_train(tp, tb, st)) return rc;
   } else {
     if (int rc = launch_train(tp, kHeadDqn, st)) return rc;

@@ -223,9 +223,10 @@ int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, ui
 int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st);
 // ---- tensor-core training pipeline (tc_train.cu) ----------------------------------------------------------------------------
 struct TcBuffers {
-  uint8_t* image; uint8_t* bwd_image;       // packed online-network images (forward K-major, backward MN-major W2)
-  float *h1, *h2, *dh2, *dh1, *dq;          // [32][rows][4] x4 (chunk-major) and [rows][16] row records
-  size_t rows;                               // allocated rows
+  uint8_t* image; uint8_t* bwd_image;       // packed online-network images (forward K-major, backward K-major W2^T)
+  float *h1, *h2, *dh1;                     // [32][rows][4] (chunk-major) activations and hidden-layer gradient
+  float* rec;                               // [rows][16] row records (tc_train.cu)
+  size_t rows;                              // allocated rows
 };
 int tc_train_init();
 int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_t st);

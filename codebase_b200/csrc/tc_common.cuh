@@ -18,7 +18,7 @@ constexpr int kOffW3Hi = kOffW2Lo + 4 * kPanelBytes, kOffW3Lo = kOffW3Hi + 4 * k
 constexpr int kOffB1 = kOffW3Lo + 4 * kHeadPanelBytes, kOffB2 = kOffB1 + kHidden * 4, kOffB3 = kOffB2 + kHidden * 4;
 constexpr int kOffW3F = kOffB3 + kHeadRows * 4;           // plain FP32 copy of W3 [8][128] (head gradient dH2 = dq x W3)
 constexpr int kImageBytes = kOffW3F + kOutPad * kHidden * 4;
-// backward image: W2 as an MN-major operand [k = out feature j2][n = in feature j1] (SWIZZLE_128B_BASE32B), hi | lo
+// backward image: W2^T as a K-major operand (rows = input features j1, K = output features j2), hi | lo
 constexpr int kBwdImageBytes = 8 * kPanelBytes;
 constexpr int kTcSmemBytes = kImageBytes + 64 + 1024;
 // TMEM columns of the row-per-lane kernels: A hi [0,128), A lo [128,256), D [256,384), head D [384,400)

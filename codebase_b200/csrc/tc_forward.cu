@@ -57,12 +57,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ theta, NetLayout l
   }
   if (i < kHeadRows) reinterpret_cast<float*>(img + kOffB3)[i] = i < lay.out ? th[lay.b3 + i] : 0.f;
   if (i < kOutPad * kHidden) reinterpret_cast<float*>(img + kOffW3F)[i] = (i >> 7) < lay.out ? th[lay.w3 + i] : 0.f;
-  if (bwd_image != nullptr && i < kHidden * kHidden) {  // W2[k = j2][n = j1], MN-major BASE32B, hi | lo
+  if (bwd_image != nullptr && i < kHidden * kHidden) {  // W2^T as a K-major operand: row n = input feature j1, feature k = output j2; hi | lo
     const int k = i >> 7, n = i & 127;
     const float x = th[lay.w2 + i], hi = tf32_rn(x);
     uint8_t* bi = bwd_image + (size_t)net * kBwdImageBytes;
-    *reinterpret_cast<float*>(bi + mn_offset(k, n, kPanelBytes)) = hi;
-    *reinterpret_cast<float*>(bi + 4 * kPanelBytes + mn_offset(k, n, kPanelBytes)) = tf32_rn(x - hi);
+    *reinterpret_cast<float*>(bi + panel_offset(n, k, kPanelBytes)) = hi;
+    *reinterpret_cast<float*>(bi + 4 * kPanelBytes + panel_offset(n, k, kPanelBytes)) = tf32_rn(x - hi);
   }
 }
 

@@ -2,47 +2,36 @@
 //
 // Same arithmetic as train_kernel<KP, kHeadDqn> (QNetwork._compute_loss + backward, marlbase/dqn/model.py:118-168), split where
 // one SM's shared memory / TMEM cannot hold every operand twice (hi / lo) at once:
-//   tc_dqn_fwd_kernel   online forward (A operand in TMEM, weights = K-major image), TD head in registers, dH2 = (dq x W3) * relu';
-//                        stores H1, H2, dH2 (FP32 rows) and dq for the next two kernels
-//   tc_dh1_kernel       dH1 = (dH2 x W2) * relu'(H1): A = dH2 in TMEM, B = W2 as an MN-major operand (SWIZZLE_128B_BASE32B image)
-//   tc_dw_kernel        dW2 | db2, dW1 | db1, dW3 (+ db3): row-streaming weight-gradient GEMMs, both operands MN-major from shared
-//                        memory, accumulators resident in TMEM across all the CTA's rows, flushed once into the per-CTA partial
+//   tc_dqn_fwd_kernel   online forward (A operand in TMEM, weights = K-major image), TD head in registers; stores H1, H2 (FP32,
+//                        chunk-major) and one 64-byte record per row: dLoss/dq[act], act, observation offset, ReLU masks of H1 / H2
+//   tc_dh1_kernel       dH1 = (dH2 x W2) * relu'(H1); dH2[r][j] = g_r W3[act_r][j] relu'(H2[r][j]) is rebuilt from the record (the TD
+//                        loss touches one output per row), so it never travels through memory; B = K-major image of W2^T
+//   tc_dw_kernel        dW2 | db2 and dW1 | db1: row-streaming TN GEMMs, both operands MN-major from shared memory, accumulators
+//                        resident in TMEM across all the CTA's rows; dW3 / db3 (one non-zero dq per row) accumulate in FP32 registers.
+//                        16 producer warps stage 16-row chunks into a two-deep ring, a 17th warp issues the MMAs (mbarrier ring)
 // The partials feed the same grad_reduce_kernel / adam_kernel as the FP32 path.
 #include "tc_common.cuh"
 
 namespace marl {
 
-constexpr int kRowRec = 16;  // floats per row record
+constexpr int kRowRec = 16;  // floats per row record: [0] g, [1] act, [2..3] observation element offset (int64), [4..7] mask1, [8..11] mask2
 
 struct TcTrainParams {
   RowPlan plan; RowSource src; NetLayout lay;
   const uint8_t* images;      // forward images [n_nets][kImageBytes]
   const uint8_t* bwd_images;  // backward images [n_nets][kBwdImageBytes]
   float* q_out;               // [rows][out] online outputs (optional)
-  // H1, H2, dH2, dH1: [32 float4 column chunks][rows][4] -- chunk-major, so that a warp whose lanes are 32 consecutive rows writes or
+  // H1, H2, dH1: [32 float4 column chunks][rows][4] -- chunk-major, so that a warp whose lanes are 32 consecutive rows writes or
   // reads 512 contiguous bytes per instruction (row-major rows of 512 B cost one cache line per lane and instruction)
-  float* h1g; float* h2g; float* dh2g; float* dh1g; size_t rows;
-  float* dqg;  // [rows][kRowRec] row records: dq[8] | ReLU mask of H1 (4 words) | observation offset (int64) | pad
+  float* h1g; float* h2g; float* dh1g; size_t rows;
+  float* rec;                 // [rows][kRowRec] row records
   const float* tq; const float* td_ext; float gamma; int double_q;
   float* scratch; int scratch_pitch; float* loss_part;
-  int debug;
 };
 
 __device__ __forceinline__ size_t dst_of(const RowPlan& plan, const RowSource& src, int net, int vr, int& agent, int& unit, int& off) {
   decode_row(plan, net, vr, agent, unit, off);
   return src.mode == 0 ? ((size_t)unit * src.N + agent) : (((size_t)agent * plan.units_per_agent + unit) * plan.unit_rows + off);
-}
-
-__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-__device__ __forceinline__ void load16(const float* src, float (&v)[16]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 x = reinterpret_cast<const float4*>(src)[j];
-    v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-  }
 }
 
 // issue helpers (one thread): 3xTF32, TS form, compile-time unrolled
@@ -59,19 +48,17 @@ __device__ __forceinline__ void issue_kmajor(uint32_t tmem, uint32_t d_col, uint
                     (term == 1 ? dlo : dhi) + (uint32_t)(((ks >> 2) * PANEL_BYTES + (ks & 3) * 32) >> 4), idesc, (term | ks) ? 1u : 0u);
 }
 
-// =====================================================================================================================
-// Thread layout of the three kernels: 16 warps.  Warp w works on TMEM lane quarter lq = w & 3 (the hardware restricts a warp to
-// lanes 32 (w % 4) .. +31) and on column quarter cq = w >> 2 of the 128 hidden features, so every SM sub-partition holds four
-// warps whose TMEM / global latencies overlap (with one warp per sub-partition the kernels sat at 15 % issue utilisation).
-// =====================================================================================================================
-
 __device__ __forceinline__ void split16(const float (&h)[16], float (&hi)[16], float (&lo)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) { hi[j] = tf32_rn(h[j]); lo[j] = tf32_rn(h[j] - hi[j]); }
 }
 
 // =====================================================================================================================
-// 1. online forward + TD head + dH2
+// Thread layout of the first two kernels: 16 warps.  Warp w works on TMEM lane quarter lq = w & 3 (the hardware restricts a warp to
+// lanes 32 (w % 4) .. +31) and on column quarter cq = w >> 2 of the 128 hidden features, so every SM sub-partition holds four
+// warps whose TMEM / global latencies overlap (with one warp per sub-partition the kernels sat at 15 % issue utilisation).
+// =====================================================================================================================
+// 1. online forward + TD head
 // =====================================================================================================================
 __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -80,8 +67,6 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   float* qs = reinterpret_cast<float*>(smem + kImageBytes + 64);   // [128][8] outputs of this tile, then loss reduction scratch
   float* carry = qs + kTileRows * kOutPad;                         // [8] outputs of the first row of the previously processed (higher) tile
-  float* gsm = carry + kOutPad;                                    // [128] d loss / d q[act] of each row
-  int* actsm = reinterpret_cast<int*>(gsm + kTileRows);            // [128] action of each row
   const int t = threadIdx.x, warp = t >> 5, lq = warp & 3, cq = warp >> 2, r = 32 * lq + (t & 31), c0 = 32 * cq;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
@@ -98,7 +83,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
   {
     const uint8_t* src = p.images + (size_t)net * kImageBytes;
     const uint32_t dst = smem_u32(smem);
-    // three cp.async groups in the order the first tile needs them: W1 + biases + W3 copy, W2, W3
+    // three cp.async groups in the order the first tile needs them: W1 + biases, W2, W3
     auto copy = [&](int begin, int end) {
       for (int i = begin / 16 + t; i < end / 16; i += kTrThreads)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
@@ -110,52 +95,70 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     copy(kOffW3Hi, kOffB1);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot, smem_base = smem_u32(smem), lane_base = tmem + ((uint32_t)(32 * lq) << 16);
-  int image_groups_pending = 3;   // block-uniform: groups not yet waited for
   const float* b1 = reinterpret_cast<const float*>(smem + kOffB1);
   const float* b2 = reinterpret_cast<const float*>(smem + kOffB2);
   const float* b3 = reinterpret_cast<const float*>(smem + kOffB3);
-  const float* w3f = reinterpret_cast<const float*>(smem + kOffW3F);
   const int D = p.src.D, A = p.lay.out, T = p.src.traj.T, B = p.plan.units_per_agent;
   const int k1steps = (D + 7) >> 3;
-  const bool x_active = 8 * cq < 8 * k1steps;   // column quarter cq stages observation columns [8 cq, 8 cq + 8)
-  uint32_t parity = 0;
-
-  // this thread's row of a tile: destination row, its 8 observation columns, and (column quarter 0) the loss-head scalars;
-  // fetched one tile ahead
-  struct RowIn { size_t dst; long long xoff; int agent, b, tt, act; float rew; uint8_t filled, done1; float x[8]; };
+  const bool x_active = cq < k1steps;   // column quarter cq stages observation columns [8 cq, 8 cq + 8)
   const float* obs_base = p.src.mode == 0 ? p.src.dense : p.src.traj.obs;
-  auto fetch = [&](int vr0, int nrows, RowIn& ri) {
-    ri.dst = 0; ri.xoff = 0; ri.agent = 0; ri.b = 0; ri.tt = 0; ri.act = 0; ri.rew = 0.f; ri.filled = 0; ri.done1 = 0;
+
+  // This thread's row of a tile is fetched one tile ahead, in two steps so that no step waits on a load it has just issued:
+  // A = decode + the episode index of the sampled unit, B (issued a barrier later) = observation columns and loss-head scalars.
+  struct RowKey { size_t dst; int agent, b, tt, ep; bool valid; };
+  struct RowIn { size_t dst; long long xoff; int agent, b, tt, act; float rew; uint8_t filled, done1; float x[8]; };
+  auto fetch_a = [&](int vr0, int nrows, RowKey& k) {
+    k.dst = 0; k.agent = 0; k.b = 0; k.tt = 0; k.ep = 0; k.valid = r < nrows;
+    if (k.valid) {
+      k.dst = dst_of(p.plan, p.src, net, vr0 + r, k.agent, k.b, k.tt);
+      if (p.src.mode != 0) k.ep = p.src.idx[k.b];
+    }
+  };
+  auto fetch_b = [&](const RowKey& k, RowIn& ri) {
+    ri.dst = k.dst; ri.xoff = 0; ri.agent = k.agent; ri.b = k.b; ri.tt = k.tt; ri.act = 0; ri.rew = 0.f; ri.filled = 0; ri.done1 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) ri.x[j] = 0.f;
-    if (r < nrows) {
-      ri.dst = dst_of(p.plan, p.src, net, vr0 + r, ri.agent, ri.b, ri.tt);
-      const float* src = row_ptr(p.src, ri.agent, ri.b, ri.tt);
+    if (k.valid) {
+      const TrajView& tv = p.src.traj;
+      const float* src = p.src.mode == 0 ? p.src.dense + ((size_t)k.b * p.src.N + k.agent) * D
+                                         : tv.obs + (((size_t)k.ep * tv.N + k.agent) * (size_t)(T + 1) + k.tt) * D;
       ri.xoff = (long long)(src - obs_base);
       if (x_active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) ri.x[j] = (8 * cq + j < D) ? src[8 * cq + j] : 0.f;
       }
-      if (cq == 0 && ri.tt < T) {
-        const TrajView& tv = p.src.traj;
-        const size_t ep = (size_t)p.src.idx[ri.b];
-        ri.act = tv.act[(ep * tv.N + ri.agent) * T + ri.tt];
-        ri.rew = tv.rew[(ep * tv.N + ri.agent) * T + ri.tt];
-        ri.filled = tv.filled[ep * T + ri.tt];   // raw bytes: converting here would wait for the loads inside the prefetch
-        ri.done1 = tv.done[ep * (T + 1) + ri.tt + 1];
+      if (cq == 0 && p.src.mode != 0 && k.tt < T) {
+        const size_t ep = (size_t)k.ep;
+        ri.act = tv.act[(ep * tv.N + k.agent) * T + k.tt];
+        ri.rew = tv.rew[(ep * tv.N + k.agent) * T + k.tt];
+        ri.filled = tv.filled[ep * T + k.tt];   // raw bytes: a conversion here would wait for the loads inside the prefetch
+        ri.done1 = tv.done[ep * (T + 1) + k.tt + 1];
       }
     }
   };
+  RowKey key_nxt;
   RowIn cur, nxt;
-  fetch(max(row_begin, row_end - kTileRows), row_end - max(row_begin, row_end - kTileRows), cur);
+  {
+    const int v0 = max(row_begin, row_end - kTileRows);
+    fetch_a(v0, row_end - v0, key_nxt);
+    fetch_b(key_nxt, cur);
+  }
+  nxt = cur;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot, smem_base = smem_u32(smem), lane_base = tmem + ((uint32_t)(32 * lq) << 16);
+  int image_groups_pending = 3;   // block-uniform: groups not yet waited for
+  uint32_t parity = 0;
+  float carry_q[kOutPad];         // thread 0: outputs of row 0 of the tile just finished, published after the next barrier
+#pragma unroll
+  for (int o = 0; o < kOutPad; ++o) carry_q[o] = 0.f;
 
   // tiles from the top of the chunk downwards (the double-Q argmax needs the next row's outputs)
   for (int vr_hi = row_end; vr_hi > row_begin; vr_hi -= kTileRows) {
     const int vr0 = max(row_begin, vr_hi - kTileRows), nrows = vr_hi - vr0;
+    const bool has_next = vr0 > row_begin;
+    if (has_next) { const int nv0 = max(row_begin, vr0 - kTileRows); fetch_a(nv0, vr0 - nv0, key_nxt); }
     if (x_active) {
       float hi[8], lo[8];
 #pragma unroll
@@ -169,17 +172,20 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     __syncthreads();
     if (t == 0) {
       tc_fence_after();
-      if (!(p.debug & 4)) issue_kmajor<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
+      issue_kmajor<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
       mma_commit(bar);
+      if (vr_hi != row_end) {   // every thread is past the previous tile's TD head: publish its first row's outputs
+#pragma unroll
+        for (int o = 0; o < kOutPad; ++o) carry[o] = carry_q[o];
+      }
     }
     const size_t dst_row = cur.dst;
     const int agent = cur.agent, b = cur.b, tt = cur.tt, act = cur.act;
     const float rew = cur.rew; const uint8_t filled_u8 = cur.filled, done1_u8 = cur.done1; const long long xoff = cur.xoff;
     // the next (lower) tile's rows: the loads stay in flight under this tile's MMAs and epilogues
-    if (vr0 > row_begin) { const int nv0 = max(row_begin, vr0 - kTileRows); fetch(nv0, vr0 - nv0, nxt); }
+    if (has_next) fetch_b(key_nxt, nxt);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
-    uint32_t h2mask = 0;
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
       const float* bias = (layer == 0 ? b1 : b2) + c0;
@@ -202,25 +208,23 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
         split16(h, hi, lo);
         tmem_st16(lane_base + kColAHi + c0 + 16 * half, hi);
         tmem_st16(lane_base + kColALo + c0 + 16 * half, lo);
-        if (r < nrows && !(p.debug & 1)) {
+        if (r < nrows) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) hg[(size_t)(8 * cq + 4 * half + j) * p.rows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
         }
       }
-      h2mask = mask;
+      if (r < nrows) reinterpret_cast<uint32_t*>(p.rec + dst_row * kRowRec)[4 + 4 * layer + cq] = mask;   // ReLU mask of this layer
       if (image_groups_pending == 2 - layer) {   // W2 before the layer-2 MMAs, W3 before the head's
         if (layer == 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         image_groups_pending = 1 - layer;
       }
-      if (layer == 0 && r < nrows) reinterpret_cast<uint32_t*>(p.dqg + dst_row * kRowRec)[8 + cq] = mask;   // ReLU mask of H1 for tc_dh1_kernel
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncthreads();
       if (t == 0) {
         tc_fence_after();
-        if (p.debug & 4) {}
-        else if (layer == 0) issue_kmajor<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
+        if (layer == 0) issue_kmajor<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
         else issue_kmajor<kHidden / 8, kHeadRows, kHeadPanelBytes>(tmem, kColDHead, smem_base + kOffW3Hi, smem_base + kOffW3Lo, kHidden / 8);
         mma_commit(bar);
       }
@@ -228,19 +232,23 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
       tc_fence_after();
     }
     // ---- outputs of this tile -> shared (next-row exchange), TD head: column quarter 0 (threads 0..127, r == t) ------------
-    float q[kOutPad];
     if (cq == 0) {
-      float v[16];
-      tmem_ld16(lane_base + kColDHead, v);
+      float q[kOutPad];
+      {
+        float v[16];
+        tmem_ld16(lane_base + kColDHead, v);
 #pragma unroll
-      for (int o = 0; o < kOutPad; ++o) q[o] = o < A ? v[o] + b3[o] : 0.f;
+        for (int o = 0; o < kOutPad; ++o) q[o] = o < A ? v[o] + b3[o] : 0.f;
+      }
       *reinterpret_cast<float4*>(qs + r * kOutPad) = make_float4(q[0], q[1], q[2], q[3]);
       *reinterpret_cast<float4*>(qs + r * kOutPad + 4) = make_float4(q[4], q[5], q[6], q[7]);
-    }
-    __syncthreads();
-    if (cq == 0) {
-      float g = 0.f;
-      if (r < nrows && !(p.debug & 8)) {
+      if (t == 0) {
+#pragma unroll
+        for (int o = 0; o < kOutPad; ++o) carry_q[o] = q[o];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four warps of column quarter 0 exchange their rows' outputs
+      if (r < nrows) {
+        float g = 0.f;
         if (p.q_out) for (int o = 0; o < A; ++o) p.q_out[dst_row * A + o] = q[o];
         if (tt < T) {
           if (p.td_ext) {
@@ -268,35 +276,9 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
             g = 2.f * delta * filled;
           }
         }
-        float dq[kOutPad];
-#pragma unroll
-        for (int o = 0; o < kOutPad; ++o) dq[o] = (o == act && tt < T) ? g : 0.f;
-        float* dqd = p.dqg + dst_row * kRowRec;
-        *reinterpret_cast<float4*>(dqd) = make_float4(dq[0], dq[1], dq[2], dq[3]);
-        *reinterpret_cast<float4*>(dqd + 4) = make_float4(dq[4], dq[5], dq[6], dq[7]);
-        *reinterpret_cast<long long*>(dqd + 12) = xoff;
-      }
-      gsm[r] = g; actsm[r] = act;
-    }
-    __syncthreads();
-    if (t == 0) {
-#pragma unroll
-      for (int o = 0; o < kOutPad; ++o) carry[o] = q[o];
-    }
-    // ---- dH2[r][j] = dq[r][act] W3[act][j] (H2[r][j] > 0): dq has one non-zero per row, the ReLU mask is still in registers ----
-    if (r < nrows && !(p.debug & 2)) {
-      const float g = gsm[r];
-      const float4* wrow = reinterpret_cast<const float4*>(w3f + actsm[r] * kHidden + c0);
-      float4* dst = reinterpret_cast<float4*>(p.dh2g) + dst_row;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const float4 w = wrow[jj];
-        float4 d;
-        d.x = (h2mask >> (4 * jj)) & 1u ? g * w.x : 0.f;
-        d.y = (h2mask >> (4 * jj + 1)) & 1u ? g * w.y : 0.f;
-        d.z = (h2mask >> (4 * jj + 2)) & 1u ? g * w.z : 0.f;
-        d.w = (h2mask >> (4 * jj + 3)) & 1u ? g * w.w : 0.f;
-        dst[(size_t)(8 * cq + jj) * p.rows] = d;
+        // the TD loss touches one output per row: dq[r][a] = g (a == act), 0 otherwise; rows at t == T carry g = 0
+        *reinterpret_cast<int4*>(p.rec + dst_row * kRowRec) =
+            make_int4(__float_as_int(g), act, (int)(uint32_t)((unsigned long long)xoff & 0xffffffffull), (int)(uint32_t)((unsigned long long)xoff >> 32));
       }
     }
     cur = nxt;
@@ -316,13 +298,17 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
 }
 
 // =====================================================================================================================
-// 2. dH1 = (dH2 x W2) * relu'(H1)
+// 2. dH1 = (dH2 x W2) * relu'(H1), dH2 rebuilt from the row records
 // =====================================================================================================================
+constexpr int kDh1W3 = kBwdImageBytes;                        // FP32 copy of W3 [8][128] behind the W2^T image
+constexpr int kDh1Bar = kDh1W3 + kOutPad * kHidden * 4;
+
 __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kBwdImageBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kDh1Bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const float4* w3f4 = reinterpret_cast<const float4*>(smem + kDh1W3);
   const int t = threadIdx.x, warp = t >> 5, lq = warp & 3, cq = warp >> 2, r = 32 * lq + (t & 31), c0 = 32 * cq;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
@@ -334,64 +320,66 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
   if (t == 0) mbar_init(bar, 1);
   {
     const uint8_t* src = p.bwd_images + (size_t)net * kBwdImageBytes;
+    const uint8_t* w3src = p.images + (size_t)net * kImageBytes + kOffW3F;
     const uint32_t dst = smem_u32(smem);
-#pragma unroll 4
     for (int i = t; i < kBwdImageBytes / 16; i += kTrThreads)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
+    for (int i = t; i < kOutPad * kHidden * 4 / 16; i += kTrThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kDh1W3 + 16u * i), "l"(w3src + 16 * (size_t)i) : "memory");
   }
-  // this thread's 32 columns of a row (8 float4), fetched one tile ahead; the weight image lands meanwhile
-  auto row_of = [&](int vr0) -> long long {
-    long long d = -1;
-    if (vr0 + r < row_end && r < kTileRows) { int a, u, o; d = (long long)dst_of(p.plan, p.src, net, vr0 + r, a, u, o); }
-    return d;
+  // this thread's row record: dLoss/dq[act], act and the two mask words of its 32 columns; fetched one tile ahead
+  struct Rec { long long d; float g; int act; uint32_t m1, m2; };
+  auto fetch = [&](int vr0, Rec& rc) {
+    rc.d = -1; rc.g = 0.f; rc.act = 0; rc.m1 = 0; rc.m2 = 0;
+    if (vr0 + r < row_end) {
+      int a, u, o;
+      rc.d = (long long)dst_of(p.plan, p.src, net, vr0 + r, a, u, o);
+      const float* rp = p.rec + rc.d * kRowRec;
+      const int2 ga = *reinterpret_cast<const int2*>(rp);
+      rc.g = __int_as_float(ga.x); rc.act = ga.y;
+      rc.m1 = reinterpret_cast<const uint32_t*>(rp)[4 + cq];
+      rc.m2 = reinterpret_cast<const uint32_t*>(rp)[8 + cq];
+    }
   };
-  auto load8 = [&](const float* base, long long d, float4 (&v)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = d >= 0 ? reinterpret_cast<const float4*>(base)[(size_t)(8 * cq + j) * p.rows + d] : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  long long d_cur = row_of(row_begin), d_nxt = -1;
-  float4 in_cur[8], in_nxt[8];
-  load8(p.dh2g, d_cur, in_cur);
+  Rec cur, nxt;
+  fetch(row_begin, cur);
+  nxt = cur;
   asm volatile("cp.async.wait_all;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot, smem_base = smem_u32(smem), lane_base = tmem + ((uint32_t)(32 * lq) << 16);
-  const uint32_t idesc = idesc_tf32_major(kHidden, 0, 1);
   uint32_t parity = 0;
   for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
+    // dH2[r][j] = g W3[act][j] (H2[r][j] > 0) for this thread's 32 columns -> A operand (hi / lo)
+    {
+      const float4* wrow = w3f4 + cur.act * (kHidden / 4) + 8 * cq;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float v[16], hi[16], lo[16];
+      for (int half = 0; half < 2; ++half) {
+        float v[16], hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 x = in_cur[4 * half + j];
-        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = wrow[4 * half + j];
+          const uint32_t m = cur.m2 >> (16 * half + 4 * j);
+          v[4 * j] = (m & 1u) ? cur.g * w.x : 0.f; v[4 * j + 1] = (m & 2u) ? cur.g * w.y : 0.f;
+          v[4 * j + 2] = (m & 4u) ? cur.g * w.z : 0.f; v[4 * j + 3] = (m & 8u) ? cur.g * w.w : 0.f;
+        }
+        split16(v, hi, lo);
+        tmem_st16(lane_base + kColAHi + c0 + 16 * half, hi);
+        tmem_st16(lane_base + kColALo + c0 + 16 * half, lo);
       }
-      split16(v, hi, lo);
-      tmem_st16(lane_base + kColAHi + c0 + 16 * half, hi);
-      tmem_st16(lane_base + kColALo + c0 + 16 * half, lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (t == 0) {
       tc_fence_after();
-      // D[r][j1] = sum_{j2} dH2[r][j2] W2[j2][j1]: k-step = 8 rows of the [k = j2][n = j1] image (1024 bytes), panels 16 KB apart
-      if (!(p.debug & 64)) {
-#pragma unroll
-      for (int term = 0; term < 3; ++term)
-#pragma unroll
-        for (int ks = 0; ks < kHidden / 8; ++ks)
-          mma_tf32_ts(tmem + kColD, tmem + (term == 0 ? kColALo : kColAHi) + ks * 8,
-                      mnmajor_desc(smem_base + (term == 1 ? 4 * kPanelBytes : 0) + ks * 1024, kPanelBytes), idesc, (term | ks) ? 1u : 0u);
-      }
+      // D[r][j1] = sum_{j2} dH2[r][j2] W2[j2][j1]: B = K-major image of W2^T (rows j1, features j2), the forward layers' MMA form
+      issue_kmajor<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base, smem_base + 4 * kPanelBytes, kHidden / 8);
       mma_commit(bar);
     }
-    // H1's ReLU mask (one word per thread, written by tc_dqn_fwd_kernel) and the next tile's dH2 are fetched while the MMAs run
-    const uint32_t m1 = d_cur >= 0 ? reinterpret_cast<const uint32_t*>(p.dqg + d_cur * kRowRec)[8 + cq] : 0u;
-    if (vr0 + kTileRows < row_end) { d_nxt = row_of(vr0 + kTileRows); load8(p.dh2g, d_nxt, in_nxt); }
+    if (vr0 + kTileRows < row_end) fetch(vr0 + kTileRows, nxt);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
     {
@@ -400,22 +388,21 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
       tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
       tmem_ld_wait(ra);
       tmem_ld_wait(rb);
-      if (d_cur >= 0) {
-        float4* gout = reinterpret_cast<float4*>(p.dh1g) + d_cur;
+      if (cur.d >= 0) {
+        float4* gout = reinterpret_cast<float4*>(p.dh1g) + cur.d;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t (&acc)[16] = j < 4 ? ra : rb;
           const int o = 4 * (j & 3);
+          const uint32_t m = cur.m1 >> (4 * j);
           float4 d;
-          d.x = (m1 >> (4 * j)) & 1u ? __uint_as_float(acc[o]) : 0.f; d.y = (m1 >> (4 * j + 1)) & 1u ? __uint_as_float(acc[o + 1]) : 0.f;
-          d.z = (m1 >> (4 * j + 2)) & 1u ? __uint_as_float(acc[o + 2]) : 0.f; d.w = (m1 >> (4 * j + 3)) & 1u ? __uint_as_float(acc[o + 3]) : 0.f;
+          d.x = (m & 1u) ? __uint_as_float(acc[o]) : 0.f; d.y = (m & 2u) ? __uint_as_float(acc[o + 1]) : 0.f;
+          d.z = (m & 4u) ? __uint_as_float(acc[o + 2]) : 0.f; d.w = (m & 8u) ? __uint_as_float(acc[o + 3]) : 0.f;
           gout[(size_t)(8 * cq + j) * p.rows] = d;
         }
       }
     }
-    d_cur = d_nxt;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) in_cur[j] = in_nxt[j];
+    cur = nxt;
   }
   tc_fence_before();
   __syncthreads();
@@ -425,17 +412,23 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
 // =====================================================================================================================
 // 3. weight gradients: row-streaming TN GEMMs, accumulators in TMEM
 // =====================================================================================================================
-constexpr int kDwThreads = 512;
+constexpr int kDwProducers = 512;                    // 16 staging warps
+constexpr int kDwThreads = kDwProducers + 32;        // + the MMA-issuing warp
 constexpr int kChunkRows = 16;                       // rows per staged chunk (two 8-row k-steps); two chunk buffers alternate
 constexpr int kChunkPanel = kChunkRows * 128;        // one 32-feature panel of a chunk
 constexpr int kOpBytes = 4 * kChunkPanel;            // a [16 rows][128 features] operand (hi or lo)
-// shared-memory map of one chunk buffer (bytes): dH2 hi|lo, H1 hi (+ ones panel) | lo (+ zero panel), dH1 hi|lo, H2 hi|lo, X hi|lo, dq hi|lo
-constexpr int kSDh2 = 0, kSH1 = kSDh2 + 2 * kOpBytes, kSDh1 = kSH1 + 2 * (kOpBytes + kChunkPanel), kSH2 = kSDh1 + 2 * kOpBytes;
-constexpr int kSX = kSH2 + 2 * kOpBytes, kSDq = kSX + 2 * kChunkPanel, kSEnd = kSDq + 2 * kChunkPanel;
-constexpr int kDwSmemBytes = 2 * kSEnd + 64 + 1024;  // two buffers + barriers / TMEM slot + alignment slack
+// shared-memory map of one chunk buffer (bytes): dH2 hi|lo, H1 hi (+ ones panel) | lo (+ zero panel), dH1 hi|lo, X hi|lo
+constexpr int kSDh2 = 0, kSH1 = kSDh2 + 2 * kOpBytes, kSDh1 = kSH1 + 2 * (kOpBytes + kChunkPanel), kSX = kSDh1 + 2 * kOpBytes;
+constexpr int kSEnd = kSX + 2 * kChunkPanel;
+constexpr int kDwW3 = 2 * kSEnd;                               // FP32 copy of W3 [8][128]
+constexpr int kDwBars = kDwW3 + kOutPad * kHidden * 4;         // full[2], empty[2], done, TMEM slot
+constexpr int kDwSmemBytes = kDwBars + 64 + 1024;              // + alignment slack
 static_assert(kSEnd % 1024 == 0, "chunk buffers must keep the 1024-byte swizzle alignment");
-// TMEM columns: dW2 | db2 [0,160), dW1 | db1 [160,192), dW3^T [192,208)
-constexpr uint32_t kColW2 = 0, kColW1 = 160, kColW3 = 192;
+// epilogue scratch (the chunk buffers are dead by then): dW3 / db3 partials of the four row groups, then one transpose tile per warp
+constexpr int kDwRed3 = 0, kDwRedG = kDwRed3 + 4 * kOutPad * kHidden * 4, kDwTile = kDwRedG + 1024, kDwTileBytes = 32 * 33 * 4;
+static_assert(kDwTile + 16 * kDwTileBytes <= 2 * kSEnd, "epilogue scratch must fit in the chunk buffers");
+// TMEM columns: dW2 | db2 [0,160), dW1 | db1 [160,192)
+constexpr uint32_t kColW2 = 0, kColW1 = 160;
 
 __device__ __forceinline__ void stage4(uint8_t* hi_img, uint8_t* lo_img, int r, int col, float4 v) {
   float4 h, l;
@@ -445,15 +438,22 @@ __device__ __forceinline__ void stage4(uint8_t* hi_img, uint8_t* lo_img, int r, 
   *reinterpret_cast<float4*>(hi_img + off) = h;
   *reinterpret_cast<float4*>(lo_img + off) = l;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSEnd);   // [0], [1]: chunk buffer consumed; [2]: everything done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDwBars);   // [2] chunk buffer staged (512 producer arrivals)
+  uint64_t* empty = full + 2;                                     // [2] chunk buffer consumed by the tensor core (tcgen05.commit)
+  uint64_t* done = full + 4;                                      // every MMA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 5);
+  const float4* w3f4 = reinterpret_cast<const float4*>(smem + kDwW3);
   // staging: warp = (4-row group, 32-feature panel), lane = (float4 column within the panel, row within the group): shared-memory
   // stores of the swizzled MN-major image stay conflict-free and every global load instruction reads eight 64-byte segments
-  const int t = threadIdx.x, warp = t >> 5, rr = 4 * (warp >> 2) + (t & 3), c4 = 8 * (warp & 3) + ((t & 31) >> 2);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, rr = 4 * ((warp >> 2) & 3) + (lane & 3), c4 = 8 * (warp & 3) + (lane >> 2);
+  const bool producer = warp < kDwProducers / 32;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   float* gs = p.scratch + (size_t)blockIdx.x * p.scratch_pitch;
@@ -465,127 +465,181 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (t == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); }
-  // constant panels of both buffers: ones column (n = 128) behind H1 hi, zeros behind H1 lo
+  if (t == 0) {
+    mbar_init(full, kDwProducers); mbar_init(full + 1, kDwProducers);
+    mbar_init(empty, 1); mbar_init(empty + 1, 1); mbar_init(done, 1);
+  }
+  // constant panels of both buffers: ones column (n = 128) behind H1 hi, zeros behind H1 lo; W3 copy
   for (int i = t; i < 2 * (kChunkPanel / 4); i += kDwThreads) {
     uint8_t* bufp = smem + (i / (kChunkPanel / 4)) * kSEnd;
     const int w = i % (kChunkPanel / 4);
     reinterpret_cast<float*>(bufp + kSH1 + kOpBytes)[w] = 0.f;
     reinterpret_cast<float*>(bufp + kSH1 + 2 * kOpBytes + kChunkPanel)[w] = 0.f;
   }
+  {
+    const float4* w3src = reinterpret_cast<const float4*>(p.images + (size_t)net * kImageBytes + kOffW3F);
+    for (int i = t; i < kOutPad * kHidden / 4; i += kDwThreads) reinterpret_cast<float4*>(smem + kDwW3)[i] = w3src[i];
+  }
   __syncthreads();
   if (t < 2 * kChunkRows) *reinterpret_cast<float*>(smem + (t / kChunkRows) * kSEnd + kSH1 + kOpBytes + mn_offset(t % kChunkRows, 0, kChunkPanel)) = 1.0f;
   const int D = p.src.D, A = p.lay.out;
   const int n_chunks = (row_end - row_begin + kChunkRows - 1) / kChunkRows, rpa = p.plan.units_per_agent * p.plan.unit_rows;
   const float* obs_base = p.src.mode == 0 ? p.src.dense : p.src.traj.obs;
-  // a chunk's data in registers: this thread's float4 of each [16][128] operand and its element of the [16][32] X / dq panels
-  struct Pre { float4 v[4]; float xv, gv; };
-  auto issue_loads = [&](int chunk, Pre& pre) {
-    const int vr = row_begin + chunk * kChunkRows + rr;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    pre.v[0] = z; pre.v[1] = z; pre.v[2] = z; pre.v[3] = z; pre.xv = 0.f; pre.gv = 0.f;
-    if (vr < row_end) {
-      size_t d;
-      if (p.src.mode == 0) { int a, u, o; d = dst_of(p.plan, p.src, net, vr, a, u, o); }
-      else { const int slot = vr / rpa; d = (size_t)p.plan.slot_agent[p.plan.slot_begin[net] + slot] * rpa + (vr - slot * rpa); }  // dst_of(), one division
-      const float* rec = p.dqg + d * kRowRec;
-      const float* xp = obs_base + *reinterpret_cast<const long long*>(rec + 12);
-      const size_t hi = (size_t)c4 * p.rows + d;
-      pre.v[0] = reinterpret_cast<const float4*>(p.dh2g)[hi];
-      pre.v[1] = reinterpret_cast<const float4*>(p.h1g)[hi];
-      pre.v[2] = reinterpret_cast<const float4*>(p.dh1g)[hi];
-      pre.v[3] = reinterpret_cast<const float4*>(p.h2g)[hi];
-      pre.xv = c4 < D ? xp[c4] : (c4 == D ? 1.f : 0.f);   // [X | 1]: the ones column carries db1
-      if (c4 < kOutPad) pre.gv = rec[c4];
-    }
-  };
-  float db3 = 0.f;  // this thread's share of sum_r dq[r][c4]
-  auto stage = [&](uint8_t* bufp, const Pre& pre) {
-    if (p.debug & 32) { db3 += pre.v[0].x + pre.v[1].x + pre.v[2].x + pre.v[3].x + pre.xv + pre.gv; return; }
-    stage4(bufp + kSDh2, bufp + kSDh2 + kOpBytes, rr, 4 * c4, pre.v[0]);
-    stage4(bufp + kSH1, bufp + kSH1 + kOpBytes + kChunkPanel, rr, 4 * c4, pre.v[1]);
-    stage4(bufp + kSDh1, bufp + kSDh1 + kOpBytes, rr, 4 * c4, pre.v[2]);
-    stage4(bufp + kSH2, bufp + kSH2 + kOpBytes, rr, 4 * c4, pre.v[3]);
-    const float xh = tf32_rn(pre.xv), gh = tf32_rn(pre.gv);
-    *reinterpret_cast<float*>(bufp + kSX + mn_offset(rr, c4, kChunkPanel)) = xh;
-    *reinterpret_cast<float*>(bufp + kSX + kChunkPanel + mn_offset(rr, c4, kChunkPanel)) = tf32_rn(pre.xv - xh);
-    *reinterpret_cast<float*>(bufp + kSDq + mn_offset(rr, c4, kChunkPanel)) = gh;
-    *reinterpret_cast<float*>(bufp + kSDq + kChunkPanel + mn_offset(rr, c4, kChunkPanel)) = tf32_rn(pre.gv - gh);
-    db3 += pre.gv;
-  };
-  Pre pre0, pre1;
-  issue_loads(0, pre0);
-  issue_loads(1, pre1);   // past the end: zeros, no loads
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot, sb = smem_u32(smem);
-  const uint32_t id_w2 = idesc_tf32_major(160, 1, 1), id_w1 = idesc_tf32_major(32, 1, 1), id_w3 = idesc_tf32_major(16, 1, 1);
-  // one thread: the 18 MMAs of a chunk (3xTF32 terms x 2 k-steps x 3 GEMMs), then a commit onto the buffer's barrier
-  auto issue_mmas = [&](uint32_t base, bool first, uint64_t* bar) {
-    tc_fence_after();
-    if (p.debug & 16) { mma_commit(bar); return; }
+
+  float acc3[kOutPad][4];   // dW3[a][4 c4 .. 4 c4 + 3] over this thread's rows; gacc: db3 (used where c4 == 0)
+  float gacc[kOutPad];
 #pragma unroll
-    for (int term = 0; term < 3; ++term) {
-      const uint32_t a_sel = term == 0 ? 1u : 0u, b_sel = term == 1 ? 1u : 0u;  // lo*hi, hi*lo, hi*hi
+  for (int a = 0; a < kOutPad; ++a) { gacc[a] = 0.f; acc3[a][0] = acc3[a][1] = acc3[a][2] = acc3[a][3] = 0.f; }
+
+  if (producer) {
+    // a chunk's data in registers: this thread's float4 of H1 / dH1 / H2, its element of the [16][32] X panel, its row's record
+    struct Pre { float4 h1, dh1, h2; float xv, g; int act; uint32_t m2; };
+    auto issue_loads = [&](int chunk, Pre& pre) {
+      const int vr = row_begin + chunk * kChunkRows + rr;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      pre.h1 = z; pre.dh1 = z; pre.h2 = z; pre.xv = 0.f; pre.g = 0.f; pre.act = 0; pre.m2 = 0;
+      if (vr < row_end) {
+        size_t d;
+        if (p.src.mode == 0) { int a, u, o; d = dst_of(p.plan, p.src, net, vr, a, u, o); }
+        else { const int slot = vr / rpa; d = (size_t)p.plan.slot_agent[p.plan.slot_begin[net] + slot] * rpa + (vr - slot * rpa); }  // dst_of(), one division
+        const float* rp = p.rec + d * kRowRec;
+        const int4 head = *reinterpret_cast<const int4*>(rp);   // g, act, observation offset
+        pre.g = __int_as_float(head.x); pre.act = head.y;
+        pre.m2 = reinterpret_cast<const uint32_t*>(rp)[8 + (c4 >> 3)];
+        const size_t hi = (size_t)c4 * p.rows + d;
+        pre.h1 = reinterpret_cast<const float4*>(p.h1g)[hi];
+        pre.dh1 = reinterpret_cast<const float4*>(p.dh1g)[hi];
+        pre.h2 = reinterpret_cast<const float4*>(p.h2g)[hi];
+        const float* xp = obs_base + (long long)(((unsigned long long)(uint32_t)head.w << 32) | (unsigned long long)(uint32_t)head.z);
+        pre.xv = c4 < D ? xp[c4] : (c4 == D ? 1.f : 0.f);   // [X | 1]: the ones column carries db1
+      }
+    };
+    auto stage = [&](uint8_t* bufp, const Pre& pre) {
+      // dH2 = g W3[act][.] relu'(H2) for this thread's four columns
+      const float4 w = w3f4[pre.act * (kHidden / 4) + c4];
+      const uint32_t m = pre.m2 >> (4 * (c4 & 7));
+      float4 dh2;
+      dh2.x = (m & 1u) ? pre.g * w.x : 0.f; dh2.y = (m & 2u) ? pre.g * w.y : 0.f;
+      dh2.z = (m & 4u) ? pre.g * w.z : 0.f; dh2.w = (m & 8u) ? pre.g * w.w : 0.f;
+      stage4(bufp + kSDh2, bufp + kSDh2 + kOpBytes, rr, 4 * c4, dh2);
+      stage4(bufp + kSH1, bufp + kSH1 + kOpBytes + kChunkPanel, rr, 4 * c4, pre.h1);
+      stage4(bufp + kSDh1, bufp + kSDh1 + kOpBytes, rr, 4 * c4, pre.dh1);
+      const float xh = tf32_rn(pre.xv);
+      *reinterpret_cast<float*>(bufp + kSX + mn_offset(rr, c4, kChunkPanel)) = xh;
+      *reinterpret_cast<float*>(bufp + kSX + kChunkPanel + mn_offset(rr, c4, kChunkPanel)) = tf32_rn(pre.xv - xh);
+      // dW3[a][j] += dq[r][a] H2[r][j], db3[a] += dq[r][a]: dq[r][.] is g at act, 0 elsewhere -- FP32 registers
 #pragma unroll
-      for (int ks = 0; ks < kChunkRows / 8; ++ks) {
-        const uint32_t ko = ks * 1024;
-        const uint32_t accf = (!first || term || ks) ? 1u : 0u;
-        // dW2[j2][j1 | 1] += dH2^T x [H1 | 1]
-        mma_tf32_ss(tmem + kColW2, mnmajor_desc(base + kSDh2 + a_sel * kOpBytes + ko, kChunkPanel),
-                    mnmajor_desc(base + kSH1 + b_sel * (kOpBytes + kChunkPanel) + ko, kChunkPanel), id_w2, accf);
-        // dW1[j1][i | 1] += dH1^T x [X | 1]
-        mma_tf32_ss(tmem + kColW1, mnmajor_desc(base + kSDh1 + a_sel * kOpBytes + ko, kChunkPanel),
-                    mnmajor_desc(base + kSX + b_sel * kChunkPanel + ko, kChunkPanel), id_w1, accf);
-        // dW3^T[j][a] += H2^T x dq
-        mma_tf32_ss(tmem + kColW3, mnmajor_desc(base + kSH2 + a_sel * kOpBytes + ko, kChunkPanel),
-                    mnmajor_desc(base + kSDq + b_sel * kChunkPanel + ko, kChunkPanel), id_w3, accf);
+      for (int a = 0; a < kOutPad; ++a) {
+        const float ga = a == pre.act ? pre.g : 0.f;
+        gacc[a] += ga;
+        acc3[a][0] = fmaf(ga, pre.h2.x, acc3[a][0]); acc3[a][1] = fmaf(ga, pre.h2.y, acc3[a][1]);
+        acc3[a][2] = fmaf(ga, pre.h2.z, acc3[a][2]); acc3[a][3] = fmaf(ga, pre.h2.w, acc3[a][3]);
+      }
+    };
+    Pre pre0, pre1;
+    issue_loads(0, pre0);
+    issue_loads(1, pre1);   // past the end: zeros, no loads
+    for (int c = 0; c < n_chunks; c += 2) {
+      // even chunk -> buffer 0 (its previous user, chunk c - 2, must have been consumed by the tensor core)
+      if (c >= 2) mbar_wait(empty, ((c >> 1) - 1) & 1);
+      stage(smem, pre0);
+      issue_loads(c + 2, pre0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(full);
+      if (c + 1 < n_chunks) {
+        if (c >= 2) mbar_wait(empty + 1, ((c >> 1) - 1) & 1);
+        stage(smem + kSEnd, pre1);
+        issue_loads(c + 3, pre1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full + 1);
       }
     }
-    mma_commit(bar);
-  };
-  uint32_t ph0 = 0, ph1 = 0;
-  for (int c = 0; c < n_chunks; c += 2) {
-    // even chunk -> buffer 0 (its previous user, chunk c - 2, must have been consumed)
-    if (c >= 2) { mbar_wait(bars, ph0); ph0 ^= 1; tc_fence_after(); }
-    stage(smem, pre0);
-    issue_loads(c + 2, pre0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    if (t == 0) issue_mmas(sb, c == 0, bars);
-    if (c + 1 < n_chunks) {
-      if (c >= 2) { mbar_wait(bars + 1, ph1); ph1 ^= 1; tc_fence_after(); }
-      stage(smem + kSEnd, pre1);
-      issue_loads(c + 3, pre1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_fence_before();
-      __syncthreads();
-      if (t == 0) issue_mmas(sb + kSEnd, false, bars + 1);
+  } else {
+    // ---- MMA warp: per chunk 12 MMAs (3xTF32 terms x 2 k-steps x 2 GEMMs), then a commit that frees the buffer ----------------
+    const uint32_t id_w2 = idesc_tf32_major(160, 1, 1), id_w1 = idesc_tf32_major(32, 1, 1);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b = c & 1;
+      mbar_wait(full + b, (c >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t base = sb + b * kSEnd;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a_sel = term == 0 ? 1u : 0u, b_sel = term == 1 ? 1u : 0u;  // lo*hi, hi*lo, hi*hi
+#pragma unroll
+          for (int ks = 0; ks < kChunkRows / 8; ++ks) {
+            const uint32_t ko = ks * 1024;
+            const uint32_t accf = (c || term || ks) ? 1u : 0u;
+            // dW2[j2][j1 | 1] += dH2^T x [H1 | 1]
+            mma_tf32_ss(tmem + kColW2, mnmajor_desc(base + kSDh2 + a_sel * kOpBytes + ko, kChunkPanel),
+                        mnmajor_desc(base + kSH1 + b_sel * (kOpBytes + kChunkPanel) + ko, kChunkPanel), id_w2, accf);
+            // dW1[j1][i | 1] += dH1^T x [X | 1]
+            mma_tf32_ss(tmem + kColW1, mnmajor_desc(base + kSDh1 + a_sel * kOpBytes + ko, kChunkPanel),
+                        mnmajor_desc(base + kSX + b_sel * kChunkPanel + ko, kChunkPanel), id_w1, accf);
+          }
+        }
+        mma_commit(empty + b);
+        if (c == n_chunks - 1) mma_commit(done);   // completes when every MMA issued above has
+      }
+      __syncwarp();
     }
   }
-  if (t == 0) mma_commit(bars + 2);   // completes when every MMA issued above has
-  mbar_wait(bars + 2, 0);
+  mbar_wait(done, 0);
   tc_fence_after();
-  // db3[a] = sum over the threads whose panel column c4 is a
+  __syncthreads();   // every producer is past its last use of the chunk buffers: they become epilogue scratch
+  // ---- dW3 / db3: sum over the four rows of a lane group (shuffles), then over the four row groups (fixed order) ------------
+  float* red3 = reinterpret_cast<float*>(smem + kDwRed3);   // [4 row groups][8][128]
+  float* redg = reinterpret_cast<float*>(smem + kDwRedG);   // [4 row groups][8]
+  if (producer) {
+#pragma unroll
+    for (int a = 0; a < kOutPad; ++a) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = acc3[a][i];
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+        acc3[a][i] = v;
+      }
+      float g = gacc[a];
+      g += __shfl_xor_sync(0xFFFFFFFFu, g, 1);
+      g += __shfl_xor_sync(0xFFFFFFFFu, g, 2);
+      gacc[a] = g;
+    }
+    if ((lane & 3) == 0) {
+      const int grp = (warp >> 2) & 3;
+#pragma unroll
+      for (int a = 0; a < kOutPad; ++a) {
+        *reinterpret_cast<float4*>(red3 + (grp * kOutPad + a) * kHidden + 4 * c4) = make_float4(acc3[a][0], acc3[a][1], acc3[a][2], acc3[a][3]);
+        if (c4 == 0) redg[grp * kOutPad + a] = gacc[a];
+      }
+    }
+  }
   __syncthreads();
-  float* red = reinterpret_cast<float*>(smem);  // operands are dead
-  if (t < kOutPad) red[t] = 0.f;
-  __syncthreads();
-  if (c4 < kOutPad) atomicAdd(red + c4, db3);   // 64 threads hold partial sums of the 8 dq columns
-  __syncthreads();
-  if (t < A) gs[p.lay.b3 + t] = red[t];
-  // ---- flush: lane j of lane quarter lq owns output feature j; the column quarters share its accumulator columns -----------
-  {
-    const int lq = warp & 3, cq = warp >> 2, j = 32 * lq + (t & 31);
+  for (int i = t; i < A * kHidden; i += kDwThreads)
+    gs[p.lay.w3 + i] = (red3[i] + red3[kOutPad * kHidden + i]) + (red3[2 * kOutPad * kHidden + i] + red3[3 * kOutPad * kHidden + i]);
+  if (t < A) gs[p.lay.b3 + t] = (redg[t] + redg[kOutPad + t]) + (redg[2 * kOutPad + t] + redg[3 * kOutPad + t]);
+  // ---- flush the TMEM accumulators: lane j of lane quarter lq owns output feature j; each warp transposes its 32 x 32 block of
+  // dW2 through shared memory so that every store instruction writes one 128-byte row segment ------------------------------------
+  if (producer) {
+    const int lq = warp & 3, cq = warp >> 2, j = 32 * lq + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(32 * lq) << 16);
+    float* tile = reinterpret_cast<float*>(smem + kDwTile + warp * kDwTileBytes);   // [32][33]
     float v[16];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       tmem_ld16(lane_base + kColW2 + 32 * cq + 16 * half, v);
-      store16(gs + p.lay.w2 + j * kHidden + 32 * cq + 16 * half, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tile[lane * 33 + 16 * half + i] = v[i];
     }
+    __syncwarp();
+    float* w2blk = gs + p.lay.w2 + (32 * lq) * kHidden + 32 * cq + lane;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) w2blk[i * kHidden] = tile[i * 33 + lane];
     if (cq == 0) {
       tmem_ld16(lane_base + kColW2 + kHidden, v);
       gs[p.lay.b2 + j] = v[0];
@@ -599,10 +653,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
         if (i < D) gs[p.lay.w1 + j * D + i] = x;
         else if (i == D) gs[p.lay.b1 + j] = x;
       }
-    } else if (cq == 2) {
-      tmem_ld16(lane_base + kColW3, v);
-#pragma unroll
-      for (int a = 0; a < kOutPad; ++a) if (a < A) gs[p.lay.w3 + a * kHidden + j] = v[a];
     }
   }
   tc_fence_before();
@@ -613,8 +663,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
 // =====================================================================================================================
 // launchers
 // =====================================================================================================================
-constexpr int kFwdTrainSmem = kImageBytes + 64 + (kTileRows * kOutPad + kOutPad + 2 * kTileRows + 8) * 4 + 1024;
-constexpr int kDh1Smem = kBwdImageBytes + 64 + 1024;
+constexpr int kFwdTrainSmem = kImageBytes + 64 + (kTileRows * kOutPad + kOutPad + 8) * 4 + 1024;
+constexpr int kDh1Smem = kDh1Bar + 64 + 1024;
 
 int tc_train_init() {
   MARL_CUDA_TRY(cudaFuncSetAttribute(tc_dqn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdTrainSmem));
@@ -628,9 +678,9 @@ int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_
   MARL_REQUIRE(tp.lay.in < kMaxObsDim, "tensor-core backward: observation width %d needs a spare column for the bias trick (max %d)", tp.lay.in, kMaxObsDim - 1);
   TcTrainParams p; memset(&p, 0, sizeof(p));
   p.plan = tp.plan; p.src = tp.src; p.lay = tp.lay; p.images = buf.image; p.bwd_images = buf.bwd_image; p.q_out = nullptr;
-  p.h1g = buf.h1; p.h2g = buf.h2; p.dh2g = buf.dh2; p.dh1g = buf.dh1; p.dqg = buf.dq; p.rows = buf.rows;
+  p.h1g = buf.h1; p.h2g = buf.h2; p.dh1g = buf.dh1; p.rec = buf.rec; p.rows = buf.rows;
   p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
-  p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part; p.debug = tc_debug_bits();
+  p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
   tc_dqn_fwd_kernel<<<grid, kTrThreads, kFwdTrainSmem, st>>>(p);
   MARL_CUDA_TRY(cudaGetLastError());
