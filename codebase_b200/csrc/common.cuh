@@ -71,6 +71,26 @@ __host__ __device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t n) {
 // uniform float in [0, 1) with 24 random bits
 __host__ __device__ __forceinline__ float u01(uint32_t u) { return (float)(u >> 8) * (1.0f / 16777216.0f); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
+// The per-update kernels form one dependency chain on one stream; each is launched with programmatic stream serialization so that
+// its CTAs are scheduled (and run their data-independent setup: TMEM allocation, barrier init) while the previous kernel drains.
+// Contract of every kernel launched through launch_pdl: no global memory access before pdl_wait(); pdl_launch_dependents() right
+// after it (when kernel K starts, K-1 has passed its wait, hence K-2 and everything before it has completed).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
+
 int check_device(int device);
 int tc_forward_enabled();
 int tc_backward_enabled();

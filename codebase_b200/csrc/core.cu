@@ -32,7 +32,7 @@ int check_device(int device) {
   return MARL_OK;
 }
 
-static int g_tc_forward = 1, g_tc_backward = 0;
+static int g_tc_forward = 1, g_tc_backward = 1;
 int tc_forward_enabled() { return g_tc_forward; }
 int tc_backward_enabled() { return g_tc_backward; }
 

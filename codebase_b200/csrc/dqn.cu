@@ -13,6 +13,8 @@ namespace marl {
 // ---- replay sampling: np.random.randint(0, len(rb), batch) with replacement (dqn/train.py:95) ------------------
 __global__ void replay_sample_kernel(uint64_t seed, uint64_t update_idx, int batch, int n_valid, int32_t* idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   if (i >= batch) return;
   const u32x4 b = philox4x32_10((uint32_t)update_idx, (uint32_t)(update_idx >> 32), (uint32_t)(i >> 2), 0u, (uint32_t)seed, (uint32_t)(seed >> 32) ^ kTagSample);
   idx[i] = (int32_t)bounded(pick(b, i & 3), (uint32_t)n_valid);
@@ -82,6 +84,8 @@ struct marl_dqn {
   uint8_t* image_bwd = nullptr;  // MN-major image of W2 (online net) for the tensor-core backward
   float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh1 = nullptr, *tc_rec = nullptr;
   bool tgt_image_current = false;
+  // online images: valid = a full pack happened and every later change of theta came from adam_kernel (which updates them in place)
+  bool image_current = false, bwd_image_current = false;
   int64_t updates = 0, last_target_update = 0;
   RowPlan train_plan; int n_loss_parts = 0;
   // optional CUDA-event timing of the training kernel (bench.py's roofline leg)
@@ -164,13 +168,15 @@ int marl_dqn_forward(marl_dqn* h, const float* obs, int32_t n_envs, int32_t use_
   const RowPlan plan = make_plan(h->ns, n_envs, 1, h->n_sm, 32);
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 0; src.dense = obs; src.E = n_envs; src.N = h->ns.n_agents; src.D = h->ns.in;
-  return forward_any(h->ns, plan, src, use_target ? h->theta_tgt : h->theta, h->image, q_out, (cudaStream_t)stream);
+  bool& current = use_target ? h->tgt_image_current : h->image_current;
+  const int rc = forward_any(h->ns, plan, src, use_target ? h->theta_tgt : h->theta, use_target ? h->image_tgt : h->image, q_out, (cudaStream_t)stream, current);
+  if (rc == MARL_OK) current = tc_forward_enabled() != 0;
+  return rc;
 }
 
 int marl_replay_sample(uint64_t seed, uint64_t update_idx, int32_t batch, int32_t n_valid, int32_t* idx_out, void* stream) {
   MARL_REQUIRE(idx_out && batch >= 1 && n_valid >= 1, "marl_replay_sample: bad argument");
-  replay_sample_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, update_idx, batch, n_valid, idx_out);
-  MARL_CUDA_TRY(cudaGetLastError());
+  MARL_CUDA_TRY(launch_pdl(replay_sample_kernel, dim3((batch + 255) / 256), dim3(256), 0, (cudaStream_t)stream, seed, update_idx, (int)batch, (int)n_valid, idx_out));
   return MARL_OK;
 }
 
@@ -193,7 +199,8 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   const float* td_ext = nullptr;
   float* loss_part = h->loss_part;
   if (h->hp.mixer == 1) {  // VDN: online Q-values of all agents first, then the agent-summed TD error
-    if (int rc = forward_any(h->ns, plan, src, h->theta, h->image, h->q_all, st)) return rc;
+    if (int rc = forward_any(h->ns, plan, src, h->theta, h->image, h->q_all, st, h->image_current)) return rc;
+    h->image_current = tc_forward_enabled() != 0;
     VdnTdParams vp; vp.q = h->q_all; vp.tq = h->tq; vp.traj = src.traj; vp.idx = episode_idx; vp.B = batch; vp.N = h->ns.n_agents; vp.A = h->ns.out;
     vp.gamma = h->hp.gamma; vp.double_q = h->hp.double_q; vp.td = h->td;
     const int vb = (batch * T + 255) / 256;
@@ -217,7 +224,10 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
       rc |= dqn_alloc(reinterpret_cast<float**>(&h->image_bwd), (size_t)h->ns.n_nets * tc_bwd_image_bytes() / 4 + 4);
       if (rc) return MARL_ENOMEM;
     }
-    if (int rc = launch_pack_weights(h->theta, h->ns.lay, h->ns.n_nets, h->image, st, h->image_bwd)) return rc;
+    if (!h->image_current || !h->bwd_image_current) {
+      if (int rc = launch_pack_weights(h->theta, h->ns.lay, h->ns.n_nets, h->image, st, h->image_bwd)) return rc;
+      h->image_current = h->bwd_image_current = true;
+    }
     TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh1 = h->tc_dh1; tb.rec = h->tc_rec; tb.rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
     if (int rc = launch_tc_dqn_train(tp, tb, st)) return rc;
   } else {
@@ -247,6 +257,13 @@ int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   ap.loss_out = loss_out ? loss_out : h->loss_dev;
   ap.sumsq_part = h->grads_are_local ? h->sumsq : nullptr; ap.n_sumsq = (int)((h->n_params + 63) / 64);
   h->grads_are_local = false;
+  if (h->image != nullptr && tc_forward_enabled()) {  // valid images stay valid: adam_kernel rewrites the entries of every parameter it steps
+    ap.image = h->image; ap.bwd_image = h->image_bwd; ap.img_lay = h->ns.lay; ap.img_nets = h->ns.n_nets;
+    ap.image_bytes = tc_image_bytes(); ap.bwd_image_bytes = tc_bwd_image_bytes();
+    if (h->image_bwd == nullptr) h->bwd_image_current = false;
+  } else {
+    h->image_current = h->bwd_image_current = false;
+  }
   return launch_adam(ap, (cudaStream_t)stream);
 }
 
@@ -292,10 +309,10 @@ int marl_dqn_timing(marl_dqn* h, int32_t enable, float* total_ms, int32_t* count
 }
 
 /* Tell the library that the caller wrote to the parameter buffers returned by marl_dqn_param_ptrs (cached derived data --
- * the packed tensor-core image of the target network -- is rebuilt on next use). */
+ * the packed tensor-core images of the online and target networks -- is rebuilt on next use). */
 int marl_dqn_params_changed(marl_dqn* h) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_params_changed: NULL handle");
-  h->tgt_image_current = false;
+  h->tgt_image_current = false; h->image_current = false; h->bwd_image_current = false;
   return MARL_OK;
 }
 

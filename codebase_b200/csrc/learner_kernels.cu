@@ -11,7 +11,7 @@
 //  adam_kernel          clip_grad_norm_ + Adam.step + update_target (marlbase/dqn/model.py:169-196).
 //
 // Persistent CTAs, one per SM (148 on B200) split across networks; FP32 FFMA register-tiled GEMMs (see mlp.cuh).
-#include "learner.cuh"
+#include "tc_common.cuh"
 
 namespace marl {
 
@@ -359,14 +359,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) train_kernel(TrainParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 64 parameters x 4 CTA-slices per block: slice q sums the partials of CTAs c0+q, c0+q+4, ... (four loads in flight per
-// thread), the four slices are combined in a fixed order through shared memory -> deterministic.  Each block also
-// leaves the sum of squares of its 64 reduced gradients in sumsq_part (single-GPU fast path of the clip in adam_kernel).
-__global__ void __launch_bounds__(256) grad_reduce_kernel(ReduceParams p) {
-  __shared__ float part[4][64];
+// 64 parameters x 16 CTA-slices per block: slice q sums the partials of CTAs c0+q, c0+q+16, ... (every load of a thread in
+// flight at once: the kernel is a latency chain otherwise), the slices are combined in a fixed order through shared memory ->
+// deterministic.  Each block also leaves the sum of squares of its 64 reduced gradients in sumsq_part (single-GPU fast path of
+// the clip in adam_kernel).
+constexpr int kReduceSlices = 16;
+__global__ void __launch_bounds__(64 * kReduceSlices) grad_reduce_kernel(ReduceParams p) {
+  __shared__ float part[kReduceSlices][64];
   __shared__ float sq[64];
   const int lane = threadIdx.x & 63, q = threadIdx.x >> 6;
   const int i = blockIdx.x * 64 + lane, n = p.n_nets * p.P;
+  pdl_wait();
+  pdl_launch_dependents();
   float s = 0.f;
   if (i < n) {
     const int net = i / p.P, j = i - net * p.P;
@@ -374,17 +378,22 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(ReduceParams p) {
     const float* base = p.scratch + j;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int c = c0 + q;
-    for (; c + 12 < c1; c += 16) {
-      a0 += base[(size_t)c * p.scratch_pitch]; a1 += base[(size_t)(c + 4) * p.scratch_pitch];
-      a2 += base[(size_t)(c + 8) * p.scratch_pitch]; a3 += base[(size_t)(c + 12) * p.scratch_pitch];
+    for (; c + 3 * kReduceSlices < c1; c += 4 * kReduceSlices) {
+      a0 += base[(size_t)c * p.scratch_pitch]; a1 += base[(size_t)(c + kReduceSlices) * p.scratch_pitch];
+      a2 += base[(size_t)(c + 2 * kReduceSlices) * p.scratch_pitch]; a3 += base[(size_t)(c + 3 * kReduceSlices) * p.scratch_pitch];
     }
-    for (; c < c1; c += 4) a0 += base[(size_t)c * p.scratch_pitch];
-    s = (a0 + a1) + (a2 + a3);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;   // up to three more partials, loaded together
+    if (c < c1) t0 = base[(size_t)c * p.scratch_pitch];
+    if (c + kReduceSlices < c1) t1 = base[(size_t)(c + kReduceSlices) * p.scratch_pitch];
+    if (c + 2 * kReduceSlices < c1) t2 = base[(size_t)(c + 2 * kReduceSlices) * p.scratch_pitch];
+    s = ((a0 + a1) + (a2 + a3)) + ((t0 + t1) + t2);
   }
   part[q][lane] = s;
   __syncthreads();
   if (q == 0) {
-    const float g = (part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]);
+    float g = 0.f;
+#pragma unroll
+    for (int k = 0; k < kReduceSlices; k += 4) g += (part[k][lane] + part[k + 1][lane]) + (part[k + 2][lane] + part[k + 3][lane]);
     if (i < n) p.grad[i] = g;
     sq[lane] = (i < n) ? g * g : 0.f;
   }
@@ -395,11 +404,14 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(ReduceParams p) {
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
     if (threadIdx.x == 0 && p.sumsq_part) p.sumsq_part[blockIdx.x] = v;
   }
-  if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 68 && p.stats) {
-    const int which = threadIdx.x - 64;
-    float t = p.stats_accumulate ? p.stats[which] : 0.f;
-    for (int c = 0; c < p.n_loss_parts; ++c) t += p.loss_part[4 * c + which];
-    p.stats[which] = t;
+  // the four loss statistics: one warp each (a serial walk over the per-CTA parts was this kernel's critical path), fixed order
+  if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 192 && p.stats) {
+    const int which = (threadIdx.x - 64) >> 5, l = threadIdx.x & 31;
+    float t = 0.f;
+    for (int c = l; c < p.n_loss_parts; c += 32) t += p.loss_part[4 * c + which];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, off);
+    if (l == 0) p.stats[which] = (p.stats_accumulate ? p.stats[which] : 0.f) + t;
   }
 }
 
@@ -408,6 +420,8 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(ReduceParams p) {
 // Every CTA recomputes the global norm in the same order (bit-identical clip coefficient on every CTA and rank).
 __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
   __shared__ float red[256];
+  pdl_wait();
+  pdl_launch_dependents();
   const float inv_fill = 1.f / p.grad[p.n + 1];
   float clip = 1.f, norm = 0.f;
   if (p.sumsq_part) {  // single-GPU: grad_reduce_kernel already left per-block sums of squares (fixed-order combine)
@@ -444,6 +458,10 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
     const float denom = sqrtf(v) / p.bc2_sqrt + p.eps;
     th = th - (p.lr / p.bc1) * (m / denom);
     p.m[i] = m; p.v[i] = v; p.theta[i] = th;
+    if (p.image != nullptr && i < p.img_nets * p.img_lay.P) {  // keep the packed tensor-core images of theta current
+      const int net = i / p.img_lay.P;
+      pack_param(p.img_lay, i - net * p.img_lay.P, th, p.image + (size_t)net * p.image_bytes, p.bwd_image ? p.bwd_image + (size_t)net * p.bwd_image_bytes : nullptr);
+    }
     const int j = i - p.tgt_begin;
     if (j >= 0 && j < p.tgt_n) {
       if (p.target_mode == 1) p.theta_tgt[j] = th;
@@ -497,14 +515,12 @@ int launch_train(const TrainParams& p, int head, cudaStream_t st) {
 
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
   const int n = p.n_nets * p.P;
-  grad_reduce_kernel<<<(n + 63) / 64, 256, 0, st>>>(p);
-  MARL_CUDA_TRY(cudaGetLastError());
+  MARL_CUDA_TRY(launch_pdl(grad_reduce_kernel, dim3((n + 63) / 64), dim3(64 * kReduceSlices), 0, st, p));
   return MARL_OK;
 }
 
 int launch_adam(const AdamParams& p, cudaStream_t st) {
-  adam_kernel<<<(p.n + 255) / 256, 256, 0, st>>>(p);
-  MARL_CUDA_TRY(cudaGetLastError());
+  MARL_CUDA_TRY(launch_pdl(adam_kernel, dim3((p.n + 255) / 256), dim3(256), 0, st, p));
   return MARL_OK;
 }
 

@@ -28,6 +28,39 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // round to TF32 (10-bit mantissa), nearest with ties away from zero: what cvt.rna.tf32.f32 computes for finite inputs, in two
 // integer instructions instead of the five the compiler emits for the cvt (its extra work is NaN / infinity handling)
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// ---- weight image --------------------------------------------------------------------------------------------------
+// element (row n, feature k) of a [rows][K] K-major SWIZZLE_128B operand -> byte offset inside its panel set
+__device__ __forceinline__ int panel_offset(int n, int k, int panel_bytes) {
+  const int p = k >> 5, c = (k >> 2) & 7, w = k & 3;
+  return p * panel_bytes + n * 128 + ((c ^ (n & 7)) << 4) + (w << 2);
+}
+// One parameter (flat index j of a network, value x) -> its entries of the packed forward image `img` and, when present, of the
+// backward image `bwd` (W2^T).  pack_weights_kernel writes whole images with it; adam_kernel keeps valid images current.
+__device__ __forceinline__ void pack_param(const NetLayout& lay, int j, float x, uint8_t* img, uint8_t* bwd) {
+  const float hi = tf32_rn(x), lo = tf32_rn(x - hi);
+  if (j < lay.b1) {
+    const int n = (j - lay.w1) / lay.in, k = (j - lay.w1) - n * lay.in, o = panel_offset(n, k, kPanelBytes);
+    *reinterpret_cast<float*>(img + kOffW1Hi + o) = hi; *reinterpret_cast<float*>(img + kOffW1Lo + o) = lo;
+  } else if (j < lay.w2) {
+    reinterpret_cast<float*>(img + kOffB1)[j - lay.b1] = x;
+  } else if (j < lay.b2) {
+    const int n = (j - lay.w2) >> 7, k = (j - lay.w2) & 127, o = panel_offset(n, k, kPanelBytes);
+    *reinterpret_cast<float*>(img + kOffW2Hi + o) = hi; *reinterpret_cast<float*>(img + kOffW2Lo + o) = lo;
+    if (bwd != nullptr) {  // W2^T as a K-major operand: row = input feature, K = output feature
+      const int ob = panel_offset(k, n, kPanelBytes);
+      *reinterpret_cast<float*>(bwd + ob) = hi; *reinterpret_cast<float*>(bwd + 4 * kPanelBytes + ob) = lo;
+    }
+  } else if (j < lay.w3) {
+    reinterpret_cast<float*>(img + kOffB2)[j - lay.b2] = x;
+  } else if (j < lay.b3) {
+    const int n = (j - lay.w3) >> 7, k = (j - lay.w3) & 127, o = panel_offset(n, k, kHeadPanelBytes);
+    *reinterpret_cast<float*>(img + kOffW3Hi + o) = hi; *reinterpret_cast<float*>(img + kOffW3Lo + o) = lo;
+    reinterpret_cast<float*>(img + kOffW3F)[j - lay.w3] = x;
+  } else if (j < lay.P) {
+    reinterpret_cast<float*>(img + kOffB3)[j - lay.b3] = x;
+  }
+}
+
 // dynamic shared memory rounded up to 1024 bytes (swizzle atoms), keeping the pointer in the shared address space so that the
 // compiler emits LDS / STS rather than generic loads and stores
 __device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) { return raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(raw) & 1023u)) & 1023u); }

@@ -19,51 +19,26 @@ namespace marl {
 size_t tc_image_bytes() { return kImageBytes; }
 size_t tc_bwd_image_bytes() { return kBwdImageBytes; }
 
-// ---- weight image --------------------------------------------------------------------------------------------------
-// element (row n, feature k) of a [rows][K] K-major operand -> byte offset inside its panel set
-__device__ __forceinline__ int panel_offset(int n, int k, int panel_bytes) {
-  const int p = k >> 5, c = (k >> 2) & 7, w = k & 3;
-  return p * panel_bytes + n * 128 + ((c ^ (n & 7)) << 4) + (w << 2);
-}
-
+// Whole images from the flat parameters: the padding (observation columns >= in, head rows >= out) is zeroed, everything else goes
+// through pack_param (tc_common.cuh).
 __global__ void pack_weights_kernel(const float* __restrict__ theta, NetLayout lay, int n_nets, uint8_t* __restrict__ image, uint8_t* __restrict__ bwd_image) {
   const int net = blockIdx.y;
   if (net >= n_nets) return;
   const float* th = theta + (size_t)net * lay.P;
   uint8_t* img = image + (size_t)net * kImageBytes;
+  uint8_t* bwd = bwd_image ? bwd_image + (size_t)net * kBwdImageBytes : nullptr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  // W1 [128][32] (zero padded beyond in), W2 [128][128], W3 [16][128] (zero rows beyond out)
-  if (i < kHidden * 32) {
-    const int n = i >> 5, k = i & 31;
-    const float x = k < lay.in ? th[lay.w1 + n * lay.in + k] : 0.f, hi = tf32_rn(x);
-    *reinterpret_cast<float*>(img + kOffW1Hi + panel_offset(n, k, kPanelBytes)) = hi;
-    *reinterpret_cast<float*>(img + kOffW1Lo + panel_offset(n, k, kPanelBytes)) = tf32_rn(x - hi);
+  if (i < kHidden * 32 && (i & 31) >= lay.in) {  // W1 [128][32]: zero columns beyond in
+    const int o = panel_offset(i >> 5, i & 31, kPanelBytes);
+    *reinterpret_cast<float*>(img + kOffW1Hi + o) = 0.f; *reinterpret_cast<float*>(img + kOffW1Lo + o) = 0.f;
   }
-  if (i < kHidden * kHidden) {
-    const int n = i >> 7, k = i & 127;
-    const float x = th[lay.w2 + i], hi = tf32_rn(x);
-    *reinterpret_cast<float*>(img + kOffW2Hi + panel_offset(n, k, kPanelBytes)) = hi;
-    *reinterpret_cast<float*>(img + kOffW2Lo + panel_offset(n, k, kPanelBytes)) = tf32_rn(x - hi);
+  if (i < kHeadRows * kHidden && (i >> 7) >= lay.out) {  // W3 [16][128]: zero rows beyond out (also in the FP32 copy [8][128])
+    const int o = panel_offset(i >> 7, i & 127, kHeadPanelBytes);
+    *reinterpret_cast<float*>(img + kOffW3Hi + o) = 0.f; *reinterpret_cast<float*>(img + kOffW3Lo + o) = 0.f;
+    if (i < kOutPad * kHidden) reinterpret_cast<float*>(img + kOffW3F)[i] = 0.f;
   }
-  if (i < kHeadRows * kHidden) {
-    const int n = i >> 7, k = i & 127;
-    const float x = n < lay.out ? th[lay.w3 + n * kHidden + k] : 0.f, hi = tf32_rn(x);
-    *reinterpret_cast<float*>(img + kOffW3Hi + panel_offset(n, k, kHeadPanelBytes)) = hi;
-    *reinterpret_cast<float*>(img + kOffW3Lo + panel_offset(n, k, kHeadPanelBytes)) = tf32_rn(x - hi);
-  }
-  if (i < kHidden) {
-    reinterpret_cast<float*>(img + kOffB1)[i] = th[lay.b1 + i];
-    reinterpret_cast<float*>(img + kOffB2)[i] = th[lay.b2 + i];
-  }
-  if (i < kHeadRows) reinterpret_cast<float*>(img + kOffB3)[i] = i < lay.out ? th[lay.b3 + i] : 0.f;
-  if (i < kOutPad * kHidden) reinterpret_cast<float*>(img + kOffW3F)[i] = (i >> 7) < lay.out ? th[lay.w3 + i] : 0.f;
-  if (bwd_image != nullptr && i < kHidden * kHidden) {  // W2^T as a K-major operand: row n = input feature j1, feature k = output j2; hi | lo
-    const int k = i >> 7, n = i & 127;
-    const float x = th[lay.w2 + i], hi = tf32_rn(x);
-    uint8_t* bi = bwd_image + (size_t)net * kBwdImageBytes;
-    *reinterpret_cast<float*>(bi + panel_offset(n, k, kPanelBytes)) = hi;
-    *reinterpret_cast<float*>(bi + 4 * kPanelBytes + panel_offset(n, k, kPanelBytes)) = tf32_rn(x - hi);
-  }
+  if (i < kHeadRows && i >= lay.out) reinterpret_cast<float*>(img + kOffB3)[i] = 0.f;
+  if (i < lay.P) pack_param(lay, i, th[i], img, bwd);
 }
 
 
@@ -99,13 +74,15 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   const int t = threadIdx.x, warp = t >> 5, lq = warp & 3, cq = warp >> 2, r = 32 * lq + (t & 31), c0 = 32 * cq;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
-  if (row_begin >= row_end) return;
+  if (row_begin >= row_end) { pdl_wait(); return; }
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) mbar_init(bar, 1);
+  pdl_wait();   // nothing above touches global memory (PDL contract, common.cuh)
+  pdl_launch_dependents();
   {  // the weight image is already in shared-memory layout: asynchronous 16-byte copies in three groups, in the order the first
      // tile needs them (W1 + biases, W2, W3), so that its first layer does not wait for the whole image
     const uint8_t* src = images + (size_t)net * kImageBytes;
@@ -136,26 +113,37 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   int image_groups_pending = 3;         // block-uniform
   uint32_t parity = 0;
   // this thread's 8 observation columns of its row (prefetched one tile ahead) and where the row's outputs go
+  // (two steps, a barrier apart, so that neither waits on a load it has just issued: A = decode + episode index, B = the columns)
   float xin[8], xnext[8];
   size_t dst_row = 0, dst_next = 0;
-  auto fetch_row = [&](int vr0, int nrows, size_t& dst, float (&x)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = 0.f;
-    if (r < nrows) {
-      int agent, unit, off;
-      decode_row(p.plan, net, vr0 + r, agent, unit, off);
-      const float* src = row_ptr(p.src, agent, unit, off);
-      dst = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent) : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
-      if (x_active) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (8 * cq + j < D) ? src[8 * cq + j] : 0.f;
-      }
+  struct RowKey { int agent, unit, off, ep; bool valid; };
+  auto fetch_a = [&](int vr0, int nrows, RowKey& k, size_t& dst) {
+    k.agent = 0; k.unit = 0; k.off = 0; k.ep = 0; k.valid = r < nrows;
+    if (k.valid) {
+      decode_row(p.plan, net, vr0 + r, k.agent, k.unit, k.off);
+      dst = p.src.mode == 0 ? ((size_t)k.unit * p.src.N + k.agent) : (((size_t)k.agent * p.plan.units_per_agent + k.unit) * p.plan.unit_rows + k.off);
+      if (p.src.mode != 0) k.ep = p.src.idx[k.unit];
     }
   };
-  fetch_row(row_begin, min(kTileRows, row_end - row_begin), dst_row, xin);
+  auto fetch_b = [&](const RowKey& k, float (&x)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    if (k.valid && x_active) {
+      const TrajView& tv = p.src.traj;
+      const float* src = p.src.mode == 0 ? p.src.dense + ((size_t)k.unit * p.src.N + k.agent) * D
+                                         : tv.obs + (((size_t)k.ep * tv.N + k.agent) * (size_t)(tv.T + 1) + k.off) * D;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (8 * cq + j < D) ? src[8 * cq + j] : 0.f;
+    }
+  };
+  RowKey key_nxt;
+  fetch_a(row_begin, min(kTileRows, row_end - row_begin), key_nxt, dst_row);
+  fetch_b(key_nxt, xin);
 
   for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
     const int nrows = min(kTileRows, row_end - vr0);
+    const bool has_next = vr0 + kTileRows < row_end;
+    if (has_next) fetch_a(vr0 + kTileRows, min(kTileRows, row_end - vr0 - kTileRows), key_nxt, dst_next);
     // ---- input row -> A operand (hi / lo), zero padded to k1steps * 8 features -----------------------------------
     if (x_active) {
       float hi[8], lo[8];
@@ -175,7 +163,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
       mma_commit(bar);
     }
     // prefetch the next tile's rows: the loads stay in flight under this tile's epilogues and MMAs
-    if (vr0 + kTileRows < row_end) fetch_row(vr0 + kTileRows, min(kTileRows, row_end - vr0 - kTileRows), dst_next, xnext);
+    if (has_next) fetch_b(key_nxt, xnext);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
     // ---- bias + ReLU, next A operand (twice: after layer 1 and after layer 2): this thread's 32 columns --------------------
@@ -244,15 +232,14 @@ int tc_forward_init() {
 }
 
 int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, uint8_t* image, cudaStream_t st, uint8_t* bwd_image) {
-  dim3 grid((kHidden * kHidden + 255) / 256, n_nets);
+  dim3 grid((lay.P + 255) / 256, n_nets);   // P > 128 * 128 >= every padded extent
   pack_weights_kernel<<<grid, 256, 0, st>>>(theta, lay, n_nets, image, bwd_image);
   MARL_CUDA_TRY(cudaGetLastError());
   return MARL_OK;
 }
 
 int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st) {
-  tc_forward_kernel<<<p.plan.cta_begin[p.plan.n_nets], kTrThreads, kTcSmemBytes, st>>>(p, images);
-  MARL_CUDA_TRY(cudaGetLastError());
+  MARL_CUDA_TRY(launch_pdl(tc_forward_kernel, dim3(p.plan.cta_begin[p.plan.n_nets]), dim3(kTrThreads), kTcSmemBytes, st, p, images));
   return MARL_OK;
 }
 

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
   cta_rows(p.plan, net, row_begin, row_end);
   float st[2] = {0.f, 0.f};
   if (row_begin >= row_end) {
+    pdl_wait();
     if (t < 4) p.loss_part[4 * blockIdx.x + t] = 0.f;
     return;
   }
@@ -80,6 +81,8 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) mbar_init(bar, 1);
+  pdl_wait();   // nothing above touches global memory
+  pdl_launch_dependents();
   {
     const uint8_t* src = p.images + (size_t)net * kImageBytes;
     const uint32_t dst = smem_u32(smem);
@@ -312,12 +315,14 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
   const int t = threadIdx.x, warp = t >> 5, lq = warp & 3, cq = warp >> 2, r = 32 * lq + (t & 31), c0 = 32 * cq;
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
-  if (row_begin >= row_end) return;
+  if (row_begin >= row_end) { pdl_wait(); return; }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) mbar_init(bar, 1);
+  pdl_wait();   // nothing above touches global memory
+  pdl_launch_dependents();
   {
     const uint8_t* src = p.bwd_images + (size_t)net * kBwdImageBytes;
     const uint8_t* w3src = p.images + (size_t)net * kImageBytes + kOffW3F;
@@ -458,6 +463,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   cta_rows(p.plan, net, row_begin, row_end);
   float* gs = p.scratch + (size_t)blockIdx.x * p.scratch_pitch;
   if (row_begin >= row_end) {
+    pdl_wait();
     for (int i = t; i < p.lay.P; i += kDwThreads) gs[i] = 0.f;
     return;
   }
@@ -476,6 +482,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
     reinterpret_cast<float*>(bufp + kSH1 + kOpBytes)[w] = 0.f;
     reinterpret_cast<float*>(bufp + kSH1 + 2 * kOpBytes + kChunkPanel)[w] = 0.f;
   }
+  pdl_wait();   // nothing above touches global memory
+  pdl_launch_dependents();
   {
     const float4* w3src = reinterpret_cast<const float4*>(p.images + (size_t)net * kImageBytes + kOffW3F);
     for (int i = t; i < kOutPad * kHidden / 4; i += kDwThreads) reinterpret_cast<float4*>(smem + kDwW3)[i] = w3src[i];
@@ -682,12 +690,9 @@ int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_
   p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
   p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
-  tc_dqn_fwd_kernel<<<grid, kTrThreads, kFwdTrainSmem, st>>>(p);
-  MARL_CUDA_TRY(cudaGetLastError());
-  tc_dh1_kernel<<<grid, kTrThreads, kDh1Smem, st>>>(p);
-  MARL_CUDA_TRY(cudaGetLastError());
-  tc_dw_kernel<<<grid, kDwThreads, kDwSmemBytes, st>>>(p);
-  MARL_CUDA_TRY(cudaGetLastError());
+  MARL_CUDA_TRY(launch_pdl(tc_dqn_fwd_kernel, dim3(grid), dim3(kTrThreads), kFwdTrainSmem, st, p));
+  MARL_CUDA_TRY(launch_pdl(tc_dh1_kernel, dim3(grid), dim3(kTrThreads), kDh1Smem, st, p));
+  MARL_CUDA_TRY(launch_pdl(tc_dw_kernel, dim3(grid), dim3(kDwThreads), kDwSmemBytes, st, p));
   return MARL_OK;
 }
 

@@ -118,6 +118,7 @@ class QNetwork:
         self.theta, self.theta_tgt, self.adam_m, self.adam_v = [nat.device_view(p.value, self.n_params, self.device) for p in ptrs[:4]]
         self.grad = nat.device_view(ptrs[4].value, self.n_params + 4, self.device)  # + (loss numerator, filled count, 2 spare)
         self.theta.copy_(init_flat_params(self.n_nets, self.in_dim, self.n_actions, use_orthogonal_init))
+        self.params_changed()
         self.hard_update()
         self._metrics = torch.zeros(6, dtype=torch.float32, device=self.device)
         self._idx = torch.zeros(self.max_batch, dtype=torch.int32, device=self.device)

@@ -174,7 +174,8 @@ int marl_dqn_destroy(marl_dqn* q);
 int marl_dqn_param_ptrs(marl_dqn* q, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad,
                         int64_t* n_params);
 int marl_dqn_sync_target(marl_dqn* q, void* stream);        /* hard_update (dqn/model.py:195-196) */
-/* call after writing through the pointers of marl_dqn_param_ptrs: cached derived data (packed target image) is rebuilt */
+/* MUST be called after writing through the pointers of marl_dqn_param_ptrs and before the next forward / update: cached derived
+ * data (the packed tensor-core images of the online and target networks) is rebuilt on next use */
 int marl_dqn_params_changed(marl_dqn* q);
 /* model.act's network pass (dqn/model.py:96-99) for E envs at once: obs device float[E][N][in] -> q float[E][N][out] */
 int marl_dqn_forward(marl_dqn* q, const float* obs, int32_t n_envs, int32_t use_target, float* q_out, void* stream);

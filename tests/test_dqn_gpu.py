@@ -64,7 +64,7 @@ def test_update_matches_reference_golden(name):
                   target_update_interval_or_tau=float(g["hp"][4]), mixer=int(g["mixer"]))
     m = _model("VDNetwork" if hp.mixer else "QNetwork", bool(int(g["n_nets"]) == 1), hp)
     assert m.n_params == g["theta0"].size
-    m.theta.copy_(torch.tensor(g["theta0"])); m.hard_update()
+    m.theta.copy_(torch.tensor(g["theta0"])); m.params_changed(); m.hard_update()
     for u in range(len(g["losses"])):
         store = {k: g[f"u{u}_{k}"] for k in ("obs", "act", "rew", "done", "filled")}
         ts = _store_to_device(store, m.device)

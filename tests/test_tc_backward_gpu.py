@@ -57,7 +57,7 @@ def test_tc_backward_matches_ffma_and_oracle(mixer, N, D, T, B, sharing):
     # perturbations from the seeded numpy stream: an unseeded CUDA draw makes the case vary from run to run, and a near-tie in the
     # double-Q argmax (GPU and oracle outputs differ by ~1e-6) then flips one target -- a 2e-5 gradient difference that is not a bug
     noise = lambda s_: torch.as_tensor(s_ * rng.standard_normal(m.theta.numel()), dtype=torch.float32).to(m.theta.device).view_as(m.theta)
-    m.theta.add_(noise(0.02)); m.hard_update(); m.theta.add_(noise(0.01))
+    m.theta.add_(noise(0.02)); m.hard_update(); m.theta.add_(noise(0.01)); m.params_changed()  # direct writes
     st = lr.DqnState(m.theta.cpu().clone(), m.theta_tgt.cpu().clone(), m.agent_net, D, A)
     s = _store(rng, 300, N, T, D, bool(mixer))
     idx = rng.integers(0, 300, size=B).astype(np.int32)

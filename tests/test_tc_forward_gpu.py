@@ -37,6 +37,7 @@ def test_dense_forward_tc_vs_ffma_vs_oracle(n_agents, D, sharing, E):
     m = QNetwork([_space(shape=(D,))] * n_agents, [_space(n=6)] * n_agents, cfg, [128, 128], sharing, False, True, "cuda", max_batch=8, max_episode_length=25)
     m.theta.mul_(1.7)  # not the orthogonal-init special case
     m.theta.add_(torch.as_tensor(0.01 * rng.standard_normal(m.theta.numel()), dtype=torch.float32).to(m.theta.device).view_as(m.theta))
+    m.params_changed()  # direct writes
     obs = torch.tensor(rng.integers(-1, 15, size=(E, n_agents, D)).astype(np.float32), device="cuda")
     _set_tc(True)
     q_tc = m.q_values(obs).cpu().numpy()

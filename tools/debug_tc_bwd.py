@@ -12,7 +12,7 @@ def run(mixer, N, D, T, B, sharing):
     hp = lr.DqnHP(mixer=mixer)
     cfg = types.SimpleNamespace(optimizer="Adam", lr=hp.lr, gamma=hp.gamma, grad_clip=hp.grad_clip, double_q=True, target_update_interval_or_tau=200, standardise_returns=False)
     m = (M.VDNetwork if mixer else M.QNetwork)([_space(shape=(D,))] * N, [_space(n=A)] * N, cfg, [128, 128], sharing, False, True, "cuda", max_batch=B, max_episode_length=T)
-    m.theta.add_(0.02 * torch.randn_like(m.theta)); m.hard_update(); m.theta.add_(0.01 * torch.randn_like(m.theta))
+    m.theta.add_(0.02 * torch.randn_like(m.theta)); m.hard_update(); m.theta.add_(0.01 * torch.randn_like(m.theta)); m.params_changed()
     s = _store(rng, 300, N, T, D, bool(mixer))
     idx = rng.integers(0, 300, size=B).astype(np.int32)
     ts = TrajStore(300, N, T, D, m.device)
