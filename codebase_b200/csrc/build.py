@@ -29,7 +29,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + sources()
+    extra = os.environ.get("MARL_NVCC_DEFINES", "").split()   # e.g. -DMARL_TC_TIMESTAMPS (profiling builds only)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + sources()
     subprocess.check_call(cmd, cwd=HERE)
     return SO
 

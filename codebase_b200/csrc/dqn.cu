@@ -84,6 +84,7 @@ struct marl_dqn {
   uint8_t* image_bwd = nullptr;  // MN-major image of W2 (online net) for the tensor-core backward
   float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh1 = nullptr, *tc_rec = nullptr;
   bool tgt_image_current = false;
+  unsigned long long* grid_barrier = nullptr; unsigned long long grid_epoch = 0;   // arrival counter of the fused reduce + Adam kernel
   // online images: valid = a full pack happened and every later change of theta came from adam_kernel (which updates them in place)
   bool image_current = false, bwd_image_current = false;
   int64_t updates = 0, last_target_update = 0;
@@ -125,6 +126,7 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   rc |= dqn_alloc(&h->tq, rows * cfg->out_dim);
   rc |= dqn_alloc(&h->loss_dev, 8);
   rc |= dqn_alloc(&h->sumsq, (size_t)(h->n_params + 63) / 64 + 1);
+  rc |= dqn_alloc(reinterpret_cast<float**>(&h->grid_barrier), 2);   // one zero-initialised 64-bit counter
   if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->image), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
@@ -141,7 +143,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
-  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec); cudaFree(h->grid_barrier);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -180,7 +182,9 @@ int marl_replay_sample(uint64_t seed, uint64_t update_idx, int32_t batch, int32_
   return MARL_OK;
 }
 
-int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, void* stream) {
+// Gradient half of an update.  rp_out == NULL: the per-CTA partials are reduced into grad[] (grad_reduce_kernel); otherwise the
+// reduction is left to the caller (fused reduce + Adam tail) and its parameters are returned.
+static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, void* stream, ReduceParams* rp_out) {
   MARL_REQUIRE(h && traj && episode_idx, "marl_dqn_update_grads: NULL argument");
   MARL_REQUIRE(batch >= 1 && batch <= h->max_batch, "marl_dqn_update_grads: batch %d exceeds max_batch %d", batch, h->max_batch);
   MARL_REQUIRE(traj->T >= 1 && traj->T <= h->max_T, "marl_dqn_update_grads: T %d exceeds max_T %d", traj->T, h->max_T);
@@ -237,14 +241,18 @@ int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t
   ReduceParams rp; rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->ns.n_nets; rp.P = h->ns.lay.P; rp.scratch_pitch = h->scratch_pitch;
   memcpy(rp.cta_begin, plan.cta_begin, sizeof(rp.cta_begin));
   rp.n_loss_parts = n_loss_parts; rp.grad = h->grad; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0; rp.sumsq_part = h->sumsq;
+  if (rp_out != nullptr) { *rp_out = rp; return MARL_OK; }
   return launch_grad_reduce(rp, st);
 }
 
-int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
-  MARL_REQUIRE(h != nullptr, "marl_dqn_update_apply: NULL handle");
-  MARL_CUDA_TRY(cudaSetDevice(h->device));
+int marl_dqn_update_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, void* stream) {
+  return dqn_grads(h, traj, episode_idx, batch, stream, nullptr);
+}
+
+// Optimiser-step parameters of the next update (advances the update counters)
+static void dqn_adam_params(marl_dqn* h, float* loss_out, AdamParams& ap) {
   h->updates += 1;
-  AdamParams ap; memset(&ap, 0, sizeof(ap)); ap.theta = h->theta; ap.theta_tgt = h->theta_tgt; ap.m = h->m; ap.v = h->v; ap.grad = h->grad; ap.n = (int)h->n_params;
+  memset(&ap, 0, sizeof(ap)); ap.theta = h->theta; ap.theta_tgt = h->theta_tgt; ap.m = h->m; ap.v = h->v; ap.grad = h->grad; ap.n = (int)h->n_params;
   ap.lr = h->hp.lr; ap.beta1 = h->hp.beta1; ap.beta2 = h->hp.beta2; ap.eps = h->hp.eps; ap.grad_clip = h->hp.grad_clip;
   ap.bc1 = (float)(1.0 - pow((double)h->hp.beta1, (double)h->updates));
   ap.bc2_sqrt = (float)sqrt(1.0 - pow((double)h->hp.beta2, (double)h->updates));
@@ -264,13 +272,26 @@ int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   } else {
     h->image_current = h->bwd_image_current = false;
   }
+}
+
+int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_update_apply: NULL handle");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  AdamParams ap;
+  dqn_adam_params(h, loss_out, ap);
   return launch_adam(ap, (cudaStream_t)stream);
 }
 
 int marl_dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, float* loss_out, void* stream) {
-  if (int rc = marl_dqn_update_grads(h, traj, episode_idx, batch, stream)) return rc;
-  h->grads_are_local = true;  // nobody touched grad between the two halves: the clip can use the reduce kernel's sums of squares
-  return marl_dqn_update_apply(h, loss_out, stream);
+  ReduceParams rp;
+  if (int rc = dqn_grads(h, traj, episode_idx, batch, stream, &rp)) return rc;
+  h->grads_are_local = true;  // nobody touches grad between the two halves: the clip can use the per-block sums of squares
+  AdamParams ap;
+  dqn_adam_params(h, loss_out, ap);
+  // one kernel for reduce + clip + Adam when its grid fits the GPU in one wave, else the two kernels
+  if (launch_reduce_adam(rp, ap, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) return MARL_OK;
+  if (int rc = launch_grad_reduce(rp, (cudaStream_t)stream)) return rc;
+  return launch_adam(ap, (cudaStream_t)stream);
 }
 
 /* n_updates back-to-back updates with on-device replay sampling: the `rb.sample(); model.update()` pair of

@@ -159,6 +159,7 @@ int learner_kernels_init(int in_dim);                       // opt in to > 48 KB
 int launch_mlp_forward(const FwdParams& p, cudaStream_t st);
 int launch_train(const TrainParams& p, int head, cudaStream_t st);
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st);
+int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
 template <int KP>

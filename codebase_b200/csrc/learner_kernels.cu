@@ -474,6 +474,93 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Single-GPU tail of an update in ONE kernel: grad_reduce_kernel's deterministic partial sums, a grid-wide barrier, then
+// adam_kernel's clip + Adam step on the gradient each thread still holds in a register.  256 parameters x 4 CTA-slices per block,
+// every load of a thread in flight at once, one wave (the launcher guarantees that all blocks are co-resident, which the hand-made
+// barrier needs; `barrier` counts block arrivals across launches and is never reset, `target` is its value once this launch has
+// fully arrived).  grad[] and the statistics are still published: metrics and the two-call API read them.
+constexpr int kFusedParams = 256, kFusedSlices = 4;
+__global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kernel(ReduceParams rp, AdamParams ap, unsigned long long* barrier, unsigned long long target) {
+  __shared__ float part[kFusedSlices][kFusedParams];
+  __shared__ float red[kFusedParams * kFusedSlices];
+  const int t = threadIdx.x, lane = t & (kFusedParams - 1), q = t / kFusedParams;
+  const int i = blockIdx.x * kFusedParams + lane, n = rp.n_nets * rp.P;
+  pdl_wait();
+  pdl_launch_dependents();
+  float s = 0.f;
+  if (i < n) {
+    const int net = i / rp.P, j = i - net * rp.P;
+    const int c0 = rp.cta_begin[net], c1 = rp.cta_begin[net + 1];
+    const float* base = rp.scratch + j;
+    for (int cb = c0 + q; cb < c1; cb += 10 * kFusedSlices) {
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) { const int c = cb + k * kFusedSlices; v[k] = c < c1 ? base[(size_t)c * rp.scratch_pitch] : 0.f; }
+      s += (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) + (v[8] + v[9]);
+    }
+  }
+  part[q][lane] = s;
+  __syncthreads();
+  float g = 0.f;
+  if (q == 0) {
+    g = (part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]);
+    if (i < n) rp.grad[i] = g; else g = 0.f;
+  }
+  red[t] = g * g;   // zero outside slice 0
+  // the four loss statistics: one warp each of block 0, fixed order
+  if (blockIdx.x == 0 && t >= kFusedParams && t < kFusedParams + 128) {
+    const int which = (t - kFusedParams) >> 5, l = t & 31;
+    float x = 0.f;
+    for (int c = l; c < rp.n_loss_parts; c += 32) x += rp.loss_part[4 * c + which];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);
+    if (l == 0) rp.stats[which] = (rp.stats_accumulate ? rp.stats[which] : 0.f) + x;
+  }
+  __syncthreads();
+  for (int k = kFusedParams / 2; k > 0; k >>= 1) { if (t < k) red[t] += red[t + k]; __syncthreads(); }
+  if (t == 0) {
+    rp.sumsq_part[blockIdx.x] = red[0];
+    __threadfence();                       // this block's sum of squares (and block 0's statistics) before its arrival
+    atomicAdd(barrier, 1ULL);
+    while (*reinterpret_cast<volatile unsigned long long*>(barrier) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- every block: global norm from the per-block sums (fixed order), clip coefficient ------------------------------------
+  float x = 0.f;
+  for (int k = t; k < (int)gridDim.x; k += kFusedParams * kFusedSlices) x += __ldcg(rp.sumsq_part + k);
+  red[t] = x;
+  __syncthreads();
+  for (int k = kFusedParams * kFusedSlices / 2; k > 0; k >>= 1) { if (t < k) red[t] += red[t + k]; __syncthreads(); }
+  const float fill = __ldcg(ap.grad + ap.n + 1), inv_fill = 1.f / fill;
+  const float norm = sqrtf(red[0]) * inv_fill;
+  float clip = 1.f;
+  if (ap.grad_clip > 0.f) clip = fminf(ap.grad_clip / (norm + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
+  if (q == 0 && i < ap.n) {
+    const float gg = g * inv_fill * clip;
+    float m = ap.m[i], v = ap.v[i], th = ap.theta[i];
+    m = m + (gg - m) * (1.f - ap.beta1);                       // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * ap.beta2 + gg * gg * (1.f - ap.beta2);             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / ap.bc2_sqrt + ap.eps;
+    th = th - (ap.lr / ap.bc1) * (m / denom);
+    ap.m[i] = m; ap.v[i] = v; ap.theta[i] = th;
+    if (ap.image != nullptr && i < ap.img_nets * ap.img_lay.P) {
+      const int net = i / ap.img_lay.P;
+      pack_param(ap.img_lay, i - net * ap.img_lay.P, th, ap.image + (size_t)net * ap.image_bytes, ap.bwd_image ? ap.bwd_image + (size_t)net * ap.bwd_image_bytes : nullptr);
+    }
+    const int j = i - ap.tgt_begin;
+    if (j >= 0 && j < ap.tgt_n) {
+      if (ap.target_mode == 1) ap.theta_tgt[j] = th;
+      else if (ap.target_mode == 2) ap.theta_tgt[j] = (1.f - ap.tau) * ap.theta_tgt[j] + ap.tau * th;
+    }
+  }
+  if (blockIdx.x == 0 && t == 0 && ap.loss_out) {
+    ap.loss_out[0] = __ldcg(ap.grad + ap.n) * inv_fill; ap.loss_out[1] = norm; ap.loss_out[2] = __ldcg(ap.grad + ap.n + 2) * inv_fill;
+    ap.loss_out[3] = __ldcg(ap.grad + ap.n + 3) * inv_fill; ap.loss_out[4] = fill; ap.loss_out[5] = 0.f;
+  }
+}
+
 // ---- launchers ------------------------------------------------------------------------------------------------
 template <int KP>
 static int init_kp() {
@@ -516,6 +603,15 @@ int launch_train(const TrainParams& p, int head, cudaStream_t st) {
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
   const int n = p.n_nets * p.P;
   MARL_CUDA_TRY(launch_pdl(grad_reduce_kernel, dim3((n + 63) / 64), dim3(64 * kReduceSlices), 0, st, p));
+  return MARL_OK;
+}
+
+// Fused tail; returns MARL_EINVAL without launching when the grid could not be co-resident (the caller then uses the two kernels).
+int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st) {
+  const int n = rp.n_nets * rp.P, grid = (n + kFusedParams - 1) / kFusedParams;
+  if (grid > 2 * n_sm || ap.n != n) return MARL_EINVAL;   // two 1024-thread blocks fit on an SM
+  *epoch += (unsigned long long)grid;
+  MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel, dim3(grid), dim3(kFusedParams * kFusedSlices), 0, st, rp, ap, barrier, *epoch));
   return MARL_OK;
 }
 

@@ -28,6 +28,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // round to TF32 (10-bit mantissa), nearest with ties away from zero: what cvt.rna.tf32.f32 computes for finite inputs, in two
 // integer instructions instead of the five the compiler emits for the cvt (its extra work is NaN / infinity handling)
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// 3xTF32 operand split: x = hi + lo with both parts representable in TF32 (lo rounded too: leaving it to the tensor core's
+// truncation was measured to make no speed difference)
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) { hi = tf32_rn(x); lo = tf32_rn(x - hi); }
 // ---- weight image --------------------------------------------------------------------------------------------------
 // element (row n, feature k) of a [rows][K] K-major SWIZZLE_128B operand -> byte offset inside its panel set
 __device__ __forceinline__ int panel_offset(int n, int k, int panel_bytes) {
@@ -60,6 +63,21 @@ __device__ __forceinline__ void pack_param(const NetLayout& lay, int j, float x,
     reinterpret_cast<float*>(img + kOffB3)[j - lay.b3] = x;
   }
 }
+
+// ---- optional phase timestamps (profiling builds: MARL_NVCC_DEFINES=-DMARL_TC_TIMESTAMPS) ------------------------------------------
+// One thread of CTA 5 records clock64() at phase boundaries into shared memory and prints the offsets when the kernel ends.
+#ifdef MARL_TC_TIMESTAMPS
+constexpr int kTsBytes = 1024;
+#define TS_DECL(ptr, thread, slot) long long* ts_ = reinterpret_cast<long long*>(ptr) + 48 * (slot); const bool ts_on_ = (int)threadIdx.x == (thread) && blockIdx.x == 5; \
+  int tsi_ = 1; if (ts_on_) { for (int i_ = 1; i_ < 48; ++i_) ts_[i_] = 0; ts_[0] = clock64(); }
+#define TS() do { if (ts_on_ && tsi_ < 48) ts_[tsi_++] = clock64(); } while (0)
+#define TS_DUMP(name) do { if (ts_on_) { printf("TS %s:", name); for (int i_ = 1; i_ < tsi_; ++i_) printf(" %lld", ts_[i_] - ts_[0]); printf("\n"); } } while (0)
+#else
+constexpr int kTsBytes = 0;
+#define TS_DECL(ptr, thread, slot)
+#define TS()
+#define TS_DUMP(name)
+#endif
 
 // dynamic shared memory rounded up to 1024 bytes (swizzle atoms), keeping the pointer in the shared address space so that the
 // compiler emits LDS / STS rather than generic loads and stores

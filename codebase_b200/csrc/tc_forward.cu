@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
     if (x_active) {
       float hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { hi[j] = tf32_rn(xin[j]); lo[j] = tf32_rn(xin[j] - hi[j]); }
+      for (int j = 0; j < 8; ++j) tf32_split(xin[j], hi[j], lo[j]);
       tmem_st8(lane_base + kColAHi + 8 * cq, hi);
       tmem_st8(lane_base + kColALo + 8 * cq, lo);
     }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float h = fmaxf(__uint_as_float(acc[j]) + bias[16 * half + j], 0.f);
-          hi[j] = tf32_rn(h); lo[j] = tf32_rn(h - hi[j]);
+          tf32_split(h, hi[j], lo[j]);
         }
         tmem_st16(lane_base + kColAHi + c0 + 16 * half, hi);
         tmem_st16(lane_base + kColALo + c0 + 16 * half, lo);
