@@ -31,6 +31,9 @@ TIME_LIMIT = 25
 LBF_KW = dict(rows=8, cols=8, n_agents=2, max_num_food=3, sight=8, time_limit=TIME_LIMIT)
 N_AGENTS, OBS_DIM, N_ACTIONS, HIDDEN = 2, 15, 6, 128
 FWD_FLOP_PER_ROW = 2 * (OBS_DIM * HIDDEN + HIDDEN * HIDDEN + HIDDEN * N_ACTIONS)  # 38 144
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload, from the ncu --set full capture summarised in
+# profiles/r1_tc_pipeline.md (cold caches: ncu flushes L2 before every kernel)
+TRAFFIC_NCU = {"tc_dqn_fwd_kernel": None, "tc_dh1_kernel": None, "tc_dw_kernel": None}
 
 
 def parse():
@@ -233,10 +236,15 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         iteration(False)
     sampler = ClockSampler(local) if rank == 0 else None
-    model.timing(True)
     ms, n_steps = timed(args.steps, False)
-    train_ms, train_n = model.timing(False)
     clocks = sampler.stop() if sampler else None
+    # roofline leg: one more iteration with the library's CUDA events around (and inside) the training pass of its first 1024
+    # updates -- outside the headline region, because in-stream events serialise launches that otherwise overlap (PDL)
+    model.timing(True)
+    iteration(False)
+    torch.cuda.synchronize()
+    train_ms, train_n = model.timing(False)
+    kernel_ms, kernel_n = model.timing_kernels()
     e2e = None
     if not args.no_e2e:
         iteration(True)
@@ -250,7 +258,7 @@ def run_b200(args):
         return
     value = n_steps / (ms / 1e3)
     rows = N_AGENTS * (T + 1) * B
-    train_flop = 3 * rows * FWD_FLOP_PER_ROW             # online forward (1x) + backward (2x) of the fused training kernel
+    train_flop = 3 * rows * FWD_FLOP_PER_ROW             # online forward (1x) + backward (2x) of one update
     train_avg_s = (train_ms / max(train_n, 1)) / 1e3
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -261,19 +269,47 @@ def run_b200(args):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    train_bytes = B * 3421 + 7 * 4 * model.n_params       # gathered episodes + parameter / Adam traffic
-    achieved = train_flop / train_avg_s / 1e12 if train_n else None
-    roofline = {"bound": "fp32-fma", "kernel": "train_kernel<16, kHeadDqn>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": (achieved / fp32_peak) if achieved else None,
-                "traffic": 5524224,  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_train_kernel_final.md)
-                "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz median SM clock sampled during the run (MEASURED_PEAKS.json holds no FP32 figure)",
-                "launch_us": 1e6 * train_avg_s, "launches_timed": train_n, "flop_per_launch": train_flop,
-                "hbm": {"achieved_gbs": (train_bytes / train_avg_s / 1e9) if train_n else None, "peak_gbs": hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
-                        "frac": (train_bytes / train_avg_s / 1e9 / hbm_peak) if train_n else None, "bytes_per_launch": train_bytes,
-                        "note": "the fused learner is compute-bound (~1 750 FLOP/B, SURVEY F7): the HBM fraction is small by construction"},
-                "bf16_tensor_peak_tflops": peaks.get("bf16_tflops_sustained")}
-    launches_per_step = 1 + 2 * T + U * 5
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1443.2)   # sustained figure: the kernel is timed inside a long step
+    if kernel_n:
+        # tensor-core training pass: three kernels; the roofline object describes the slowest one
+        names = ["tc_dqn_fwd_kernel", "tc_dh1_kernel", "tc_dw_kernel"]
+        D_in, A_out = 15, 6
+        flops = [rows * FWD_FLOP_PER_ROW,                                  # online forward
+                 rows * 2 * 128 * 128,                                     # dH1 = dH2 x W2
+                 rows * 2 * (128 * 128 + 128 * D_in + A_out * 128 + 128 + 128 + A_out)]   # dW2, dW1, dW3 and the bias sums
+        # algorithmic HBM bytes per update: H1, H2 written + read, dH1 written + read (FP32), 64-byte row records written + read twice,
+        # gathered observations, target outputs, per-CTA gradient partials
+        inter = [rows * (2 * 512 + 64) + rows * D_in * 4 + rows * A_out * 4, rows * (512 + 64), rows * (3 * 512 + 64 + D_in * 4) + n_sm * 4 * (model.n_params // 2)]
+        us = [1e3 * m / kernel_n for m in kernel_ms]
+        k = max(range(3), key=lambda i: us[i])
+        achieved = flops[k] / (us[k] * 1e-6) / 1e12
+        roofline = {"bound": "tensor", "kernel": names[k], "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                    "traffic": TRAFFIC_NCU.get(names[k]),   # dram bytes of one launch, ncu --set full (profiles/r1_tc_pipeline.md)
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; TF32 runs at half of it and 3xTF32 needs three MMAs per "
+                                   "FP32-accurate product: the FP32-equivalent ceiling of this arithmetic is peak / 6)",
+                    "fp32_equivalent_peak": tensor_peak / 6, "frac_of_fp32_equivalent_peak": achieved / (tensor_peak / 6),
+                    "launch_us": us[k], "launches_timed": kernel_n, "flop_per_launch": flops[k],
+                    "kernels": {names[i]: {"launch_us": us[i], "flop": flops[i], "tflops": flops[i] / (us[i] * 1e-6) / 1e12,
+                                           "algorithmic_bytes": inter[i], "gbs": inter[i] / (us[i] * 1e-6) / 1e9, "hbm_frac": inter[i] / (us[i] * 1e-6) / 1e9 / hbm_peak}
+                                for i in range(3)},
+                    "training_pass": {"launch_us": 1e6 * train_avg_s, "flop": train_flop, "tflops": train_flop / train_avg_s / 1e12,
+                                      "frac_of_fp32_cuda_core_peak": train_flop / train_avg_s / 1e12 / fp32_peak, "fp32_cuda_core_peak": fp32_peak,
+                                      "note": "events between the three kernels serialise them; the headline run overlaps their heads and tails (PDL)"},
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"}
+    else:
+        train_bytes = B * 3421 + 7 * 4 * model.n_params       # gathered episodes + parameter / Adam traffic
+        achieved = train_flop / train_avg_s / 1e12 if train_n else None
+        roofline = {"bound": "fp32-fma", "kernel": "train_kernel<16, kHeadDqn>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": (achieved / fp32_peak) if achieved else None,
+                    "traffic": 5524224,  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_train_kernel_final.md)
+                    "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz median SM clock sampled during the run (MEASURED_PEAKS.json holds no FP32 figure)",
+                    "launch_us": 1e6 * train_avg_s, "launches_timed": train_n, "flop_per_launch": train_flop,
+                    "hbm": {"achieved_gbs": (train_bytes / train_avg_s / 1e9) if train_n else None, "peak_gbs": hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
+                            "frac": (train_bytes / train_avg_s / 1e9 / hbm_peak) if train_n else None, "bytes_per_launch": train_bytes,
+                            "note": "the fused learner is compute-bound (~1 750 FLOP/B, SURVEY F7): the HBM fraction is small by construction"},
+                    "bf16_tensor_peak_tflops": peaks.get("bf16_tflops_sustained")}
+    launches_per_step = 1 + 2 * T + U * (6 if kernel_n else 4)   # reset, per env step (forward, env), per update (sample, target forward, 3-kernel pass | fused kernel, reduce + Adam)
     line = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

@@ -82,7 +82,7 @@ struct marl_dqn {
   uint8_t* image = nullptr;      // packed weight images for the tensor-core forward path (scratch, rebuilt per call)
   uint8_t* image_tgt = nullptr;  // image of theta_tgt, rebuilt only when the target network changed
   uint8_t* image_bwd = nullptr;  // MN-major image of W2 (online net) for the tensor-core backward
-  float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh1 = nullptr, *tc_rec = nullptr;
+  float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh1 = nullptr, *tc_rec = nullptr, *tc_x = nullptr;
   bool tgt_image_current = false;
   unsigned long long* grid_barrier = nullptr; unsigned long long grid_epoch = 0;   // arrival counter of the fused reduce + Adam kernel
   // online images: valid = a full pack happened and every later change of theta came from adam_kernel (which updates them in place)
@@ -90,7 +90,8 @@ struct marl_dqn {
   int64_t updates = 0, last_target_update = 0;
   RowPlan train_plan; int n_loss_parts = 0;
   // optional CUDA-event timing of the training kernel (bench.py's roofline leg)
-  bool timing = false; std::vector<cudaEvent_t> ev; int ev_used = 0;
+  // measurement hook: 4 events per timed update (before the training pass, after each of its kernels; the FP32 path uses 0 and 3)
+  bool timing = false; std::vector<cudaEvent_t> ev; int ev_used = 0; bool ev_split = false;
 };
 static const int kTimingPairs = 1024;
 
@@ -143,7 +144,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
-  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec); cudaFree(h->grid_barrier);
+  cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec); cudaFree(h->tc_x); cudaFree(h->grid_barrier);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -218,13 +219,13 @@ static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* epi
   tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext;
   tp.gamma = h->hp.gamma; tp.double_q = h->hp.double_q; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch; tp.loss_part = loss_part;
   const bool rec = h->timing && h->ev_used < kTimingPairs;
-  if (rec) cudaEventRecord(h->ev[2 * h->ev_used], st);
+  if (rec) cudaEventRecord(h->ev[4 * h->ev_used], st);
   if (tc_backward_enabled() && h->ns.in < kMaxObsDim) {
     if (!h->tc_h1) {  // intermediates of the tensor-core pipeline, allocated on first use
       const size_t rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
       int rc = 0;
       rc |= dqn_alloc(&h->tc_h1, rows * kHidden); rc |= dqn_alloc(&h->tc_h2, rows * kHidden);
-      rc |= dqn_alloc(&h->tc_dh1, rows * kHidden); rc |= dqn_alloc(&h->tc_rec, rows * 16 /* kRowRec */);
+      rc |= dqn_alloc(&h->tc_dh1, rows * kHidden); rc |= dqn_alloc(&h->tc_rec, rows * 16 /* kRowRec */); rc |= dqn_alloc(&h->tc_x, rows * kMaxObsDim);
       rc |= dqn_alloc(reinterpret_cast<float**>(&h->image_bwd), (size_t)h->ns.n_nets * tc_bwd_image_bytes() / 4 + 4);
       if (rc) return MARL_ENOMEM;
     }
@@ -232,12 +233,13 @@ static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* epi
       if (int rc = launch_pack_weights(h->theta, h->ns.lay, h->ns.n_nets, h->image, st, h->image_bwd)) return rc;
       h->image_current = h->bwd_image_current = true;
     }
-    TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh1 = h->tc_dh1; tb.rec = h->tc_rec; tb.rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
-    if (int rc = launch_tc_dqn_train(tp, tb, st)) return rc;
+    TcBuffers tb; tb.image = h->image; tb.bwd_image = h->image_bwd; tb.h1 = h->tc_h1; tb.h2 = h->tc_h2; tb.dh1 = h->tc_dh1; tb.rec = h->tc_rec; tb.x = h->tc_x; tb.rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
+    if (int rc = launch_tc_dqn_train(tp, tb, st, rec ? &h->ev[4 * h->ev_used + 1] : nullptr)) return rc;
+    if (rec) h->ev_split = true;
   } else {
     if (int rc = launch_train(tp, kHeadDqn, st)) return rc;
   }
-  if (rec) { cudaEventRecord(h->ev[2 * h->ev_used + 1], st); h->ev_used += 1; }
+  if (rec) { cudaEventRecord(h->ev[4 * h->ev_used + 3], st); h->ev_used += 1; }
   ReduceParams rp; rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->ns.n_nets; rp.P = h->ns.lay.P; rp.scratch_pitch = h->scratch_pitch;
   memcpy(rp.cta_begin, plan.cta_begin, sizeof(rp.cta_begin));
   rp.n_loss_parts = n_loss_parts; rp.grad = h->grad; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0; rp.sumsq_part = h->sumsq;
@@ -313,15 +315,15 @@ int marl_dqn_timing(marl_dqn* h, int32_t enable, float* total_ms, int32_t* count
   MARL_REQUIRE(h != nullptr, "marl_dqn_timing: NULL handle");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   if (enable) {
-    if (h->ev.empty()) { h->ev.resize(2 * kTimingPairs); for (auto& e : h->ev) MARL_CUDA_TRY(cudaEventCreate(&e)); }
-    h->ev_used = 0; h->timing = true;
+    if (h->ev.empty()) { h->ev.resize(4 * kTimingPairs); for (auto& e : h->ev) MARL_CUDA_TRY(cudaEventCreate(&e)); }
+    h->ev_used = 0; h->timing = true; h->ev_split = false;
     return MARL_OK;
   }
   h->timing = false;
   float tot = 0.f;
   for (int i = 0; i < h->ev_used; ++i) {
-    MARL_CUDA_TRY(cudaEventSynchronize(h->ev[2 * i + 1]));
-    float ms = 0.f; MARL_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]));
+    MARL_CUDA_TRY(cudaEventSynchronize(h->ev[4 * i + 3]));
+    float ms = 0.f; MARL_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[4 * i], h->ev[4 * i + 3]));
     tot += ms;
   }
   if (total_ms) *total_ms = tot;
@@ -334,6 +336,26 @@ int marl_dqn_timing(marl_dqn* h, int32_t enable, float* total_ms, int32_t* count
 int marl_dqn_params_changed(marl_dqn* h) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_params_changed: NULL handle");
   h->tgt_image_current = false; h->image_current = false; h->bwd_image_current = false;
+  return MARL_OK;
+}
+
+/* Per-kernel split of the launches timed by the last marl_dqn_timing(1) .. marl_dqn_timing(0) window: summed CUDA-event durations of
+ * the three kernels of the tensor-core training pass (online forward + TD head, dH1, weight gradients).  *count = 0 when the window
+ * ran the single fused FP32 kernel instead. */
+int marl_dqn_timing_kernels(marl_dqn* h, float* ms3, int32_t* count) {
+  MARL_REQUIRE(h != nullptr && ms3 != nullptr, "marl_dqn_timing_kernels: NULL argument");
+  MARL_REQUIRE(!h->timing, "marl_dqn_timing_kernels: call marl_dqn_timing(q, 0, ...) first");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  if (count) *count = h->ev_split ? h->ev_used : 0;
+  if (!h->ev_split) return MARL_OK;
+  for (int i = 0; i < h->ev_used; ++i) {
+    MARL_CUDA_TRY(cudaEventSynchronize(h->ev[4 * i + 3]));
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f; MARL_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[4 * i + k], h->ev[4 * i + k + 1]));
+      ms3[k] += ms;
+    }
+  }
   return MARL_OK;
 }
 

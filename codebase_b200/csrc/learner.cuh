@@ -229,10 +229,11 @@ struct TcBuffers {
   uint8_t* image; uint8_t* bwd_image;       // packed online-network images (forward K-major, backward K-major W2^T)
   float *h1, *h2, *dh1;                     // [32][rows][4] (chunk-major) activations and hidden-layer gradient
   float* rec;                               // [rows][16] row records (tc_train.cu)
+  float* x;                                 // [rows][kMaxObsDim] gathered observation rows
   size_t rows;                              // allocated rows
 };
 int tc_train_init();
-int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_t st);
+int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_t st, cudaEvent_t* between = nullptr);  // between[2]: recorded after kernels 1 and 2
 // tc_forward_enabled(): process-wide switch (marl_set_option("tensor_core_forward", 0|1)), declared in common.cuh
 
 // Forward pass through whichever implementation is selected.  `image` is scratch for the packed weights (n_nets images);

@@ -3,7 +3,7 @@
 // Same arithmetic as train_kernel<KP, kHeadDqn> (QNetwork._compute_loss + backward, marlbase/dqn/model.py:118-168), split where
 // one SM's shared memory / TMEM cannot hold every operand twice (hi / lo) at once:
 //   tc_dqn_fwd_kernel   online forward (A operand in TMEM, weights = K-major image), TD head in registers; stores H1, H2 (FP32,
-//                        chunk-major) and one 64-byte record per row: dLoss/dq[act], act, observation offset, ReLU masks of H1 / H2
+//                        chunk-major), the gathered observation row and one 64-byte record per row: dLoss/dq[act], act, ReLU masks of H1 / H2
 //   tc_dh1_kernel       dH1 = (dH2 x W2) * relu'(H1); dH2[r][j] = g_r W3[act_r][j] relu'(H2[r][j]) is rebuilt from the record (the TD
 //                        loss touches one output per row), so it never travels through memory; B = K-major image of W2^T
 //   tc_dw_kernel        dW2 | db2 and dW1 | db1: row-streaming TN GEMMs, both operands MN-major from shared memory, accumulators
@@ -14,7 +14,7 @@
 
 namespace marl {
 
-constexpr int kRowRec = 16;  // floats per row record: [0] g, [1] act, [2..3] observation element offset (int64), [4..7] mask1, [8..11] mask2
+constexpr int kRowRec = 16;  // floats per row record: [0] g, [1] act, [2..3] spare, [4..7] mask1, [8..11] mask2
 
 struct TcTrainParams {
   RowPlan plan; RowSource src; NetLayout lay;
@@ -25,6 +25,8 @@ struct TcTrainParams {
   // reads 512 contiguous bytes per instruction (row-major rows of 512 B cost one cache line per lane and instruction)
   float* h1g; float* h2g; float* dh1g; size_t rows;
   float* rec;                 // [rows][kRowRec] row records
+  float* xg;                  // [rows][kMaxObsDim] gathered observation rows (zero padded to the staged width): the weight-gradient
+                              // kernel reads them without chasing the episode index again
   const float* tq; const float* td_ext; float gamma; int double_q;
   float* scratch; int scratch_pitch; float* loss_part;
 };
@@ -104,12 +106,11 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
   const int D = p.src.D, A = p.lay.out, T = p.src.traj.T, B = p.plan.units_per_agent;
   const int k1steps = (D + 7) >> 3;
   const bool x_active = cq < k1steps;   // column quarter cq stages observation columns [8 cq, 8 cq + 8)
-  const float* obs_base = p.src.mode == 0 ? p.src.dense : p.src.traj.obs;
 
   // This thread's row of a tile is fetched one tile ahead, in two steps so that no step waits on a load it has just issued:
   // A = decode + the episode index of the sampled unit, B (issued a barrier later) = observation columns and loss-head scalars.
   struct RowKey { size_t dst; int agent, b, tt, ep; bool valid; };
-  struct RowIn { size_t dst; long long xoff; int agent, b, tt, act; float rew; uint8_t filled, done1; float x[8]; };
+  struct RowIn { size_t dst; int agent, b, tt, act; float rew; uint8_t filled, done1; float x[8]; };
   auto fetch_a = [&](int vr0, int nrows, RowKey& k) {
     k.dst = 0; k.agent = 0; k.b = 0; k.tt = 0; k.ep = 0; k.valid = r < nrows;
     if (k.valid) {
@@ -118,14 +119,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     }
   };
   auto fetch_b = [&](const RowKey& k, RowIn& ri) {
-    ri.dst = k.dst; ri.xoff = 0; ri.agent = k.agent; ri.b = k.b; ri.tt = k.tt; ri.act = 0; ri.rew = 0.f; ri.filled = 0; ri.done1 = 0;
+    ri.dst = k.dst; ri.agent = k.agent; ri.b = k.b; ri.tt = k.tt; ri.act = 0; ri.rew = 0.f; ri.filled = 0; ri.done1 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) ri.x[j] = 0.f;
     if (k.valid) {
       const TrajView& tv = p.src.traj;
       const float* src = p.src.mode == 0 ? p.src.dense + ((size_t)k.b * p.src.N + k.agent) * D
                                          : tv.obs + (((size_t)k.ep * tv.N + k.agent) * (size_t)(T + 1) + k.tt) * D;
-      ri.xoff = (long long)(src - obs_base);
       if (x_active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) ri.x[j] = (8 * cq + j < D) ? src[8 * cq + j] : 0.f;
@@ -168,6 +168,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
       for (int j = 0; j < 8; ++j) { hi[j] = tf32_rn(cur.x[j]); lo[j] = tf32_rn(cur.x[j] - hi[j]); }
       tmem_st8(lane_base + kColAHi + 8 * cq, hi);
       tmem_st8(lane_base + kColALo + 8 * cq, lo);
+      if (r < nrows) {
+        float4* xo = reinterpret_cast<float4*>(p.xg + cur.dst * kMaxObsDim + 8 * cq);
+        xo[0] = make_float4(cur.x[0], cur.x[1], cur.x[2], cur.x[3]); xo[1] = make_float4(cur.x[4], cur.x[5], cur.x[6], cur.x[7]);
+      }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     if (image_groups_pending == 3) { asm volatile("cp.async.wait_group 2;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); image_groups_pending = 2; }
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     }
     const size_t dst_row = cur.dst;
     const int agent = cur.agent, b = cur.b, tt = cur.tt, act = cur.act;
-    const float rew = cur.rew; const uint8_t filled_u8 = cur.filled, done1_u8 = cur.done1; const long long xoff = cur.xoff;
+    const float rew = cur.rew; const uint8_t filled_u8 = cur.filled, done1_u8 = cur.done1;
     // the next (lower) tile's rows: the loads stay in flight under this tile's MMAs and epilogues
     if (has_next) fetch_b(key_nxt, nxt);
     mbar_wait(bar, parity); parity ^= 1;
@@ -280,8 +284,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
           }
         }
         // the TD loss touches one output per row: dq[r][a] = g (a == act), 0 otherwise; rows at t == T carry g = 0
-        *reinterpret_cast<int4*>(p.rec + dst_row * kRowRec) =
-            make_int4(__float_as_int(g), act, (int)(uint32_t)((unsigned long long)xoff & 0xffffffffull), (int)(uint32_t)((unsigned long long)xoff >> 32));
+        *reinterpret_cast<int2*>(p.rec + dst_row * kRowRec) = make_int2(__float_as_int(g), act);
       }
     }
     cur = nxt;
@@ -492,7 +495,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   if (t < 2 * kChunkRows) *reinterpret_cast<float*>(smem + (t / kChunkRows) * kSEnd + kSH1 + kOpBytes + mn_offset(t % kChunkRows, 0, kChunkPanel)) = 1.0f;
   const int D = p.src.D, A = p.lay.out;
   const int n_chunks = (row_end - row_begin + kChunkRows - 1) / kChunkRows, rpa = p.plan.units_per_agent * p.plan.unit_rows;
-  const float* obs_base = p.src.mode == 0 ? p.src.dense : p.src.traj.obs;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -507,6 +509,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   if (producer) {
     // a chunk's data in registers: this thread's float4 of H1 / dH1 / H2, its element of the [16][32] X panel, its row's record
     struct Pre { float4 h1, dh1, h2; float xv, g; int act; uint32_t m2; };
+    int slot = row_begin / rpa, slot_end = (slot + 1) * rpa;
+    long long slot_delta = (long long)(p.plan.slot_agent[p.plan.slot_begin[net] + slot] - slot) * rpa;
     auto issue_loads = [&](int chunk, Pre& pre) {
       const int vr = row_begin + chunk * kChunkRows + rr;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -514,17 +518,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
       if (vr < row_end) {
         size_t d;
         if (p.src.mode == 0) { int a, u, o; d = dst_of(p.plan, p.src, net, vr, a, u, o); }
-        else { const int slot = vr / rpa; d = (size_t)p.plan.slot_agent[p.plan.slot_begin[net] + slot] * rpa + (vr - slot * rpa); }  // dst_of(), one division
+        else {  // dst_of() without its divisions: this thread's rows only move forward, the agent slot changes every rpa rows
+          while (vr >= slot_end) { ++slot; slot_end += rpa; slot_delta = (long long)(p.plan.slot_agent[p.plan.slot_begin[net] + slot] - slot) * rpa; }
+          d = (size_t)(vr + slot_delta);
+        }
         const float* rp = p.rec + d * kRowRec;
-        const int4 head = *reinterpret_cast<const int4*>(rp);   // g, act, observation offset
+        const int2 head = *reinterpret_cast<const int2*>(rp);   // g, act
         pre.g = __int_as_float(head.x); pre.act = head.y;
         pre.m2 = reinterpret_cast<const uint32_t*>(rp)[8 + (c4 >> 3)];
         const size_t hi = (size_t)c4 * p.rows + d;
         pre.h1 = reinterpret_cast<const float4*>(p.h1g)[hi];
         pre.dh1 = reinterpret_cast<const float4*>(p.dh1g)[hi];
         pre.h2 = reinterpret_cast<const float4*>(p.h2g)[hi];
-        const float* xp = obs_base + (long long)(((unsigned long long)(uint32_t)head.w << 32) | (unsigned long long)(uint32_t)head.z);
-        pre.xv = c4 < D ? xp[c4] : (c4 == D ? 1.f : 0.f);   // [X | 1]: the ones column carries db1
+        pre.xv = c4 < D ? p.xg[d * kMaxObsDim + c4] : (c4 == D ? 1.f : 0.f);   // [X | 1]: the ones column carries db1
       }
     };
     auto stage = [&](uint8_t* bufp, const Pre& pre) {
@@ -682,16 +688,18 @@ int tc_train_init() {
 }
 
 // all three kernels walk the same episode-aligned row split, so the per-CTA partials line up with ReduceParams::cta_begin
-int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_t st) {
+int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_t st, cudaEvent_t* between) {
   MARL_REQUIRE(tp.lay.in < kMaxObsDim, "tensor-core backward: observation width %d needs a spare column for the bias trick (max %d)", tp.lay.in, kMaxObsDim - 1);
   TcTrainParams p; memset(&p, 0, sizeof(p));
   p.plan = tp.plan; p.src = tp.src; p.lay = tp.lay; p.images = buf.image; p.bwd_images = buf.bwd_image; p.q_out = nullptr;
-  p.h1g = buf.h1; p.h2g = buf.h2; p.dh1g = buf.dh1; p.rec = buf.rec; p.rows = buf.rows;
+  p.h1g = buf.h1; p.h2g = buf.h2; p.dh1g = buf.dh1; p.rec = buf.rec; p.xg = buf.x; p.rows = buf.rows;
   p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
   p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
   MARL_CUDA_TRY(launch_pdl(tc_dqn_fwd_kernel, dim3(grid), dim3(kTrThreads), kFwdTrainSmem, st, p));
+  if (between) MARL_CUDA_TRY(cudaEventRecord(between[0], st));
   MARL_CUDA_TRY(launch_pdl(tc_dh1_kernel, dim3(grid), dim3(kTrThreads), kDh1Smem, st, p));
+  if (between) MARL_CUDA_TRY(cudaEventRecord(between[1], st));
   MARL_CUDA_TRY(launch_pdl(tc_dw_kernel, dim3(grid), dim3(kDwThreads), kDwSmemBytes, st, p));
   return MARL_OK;
 }

@@ -198,6 +198,9 @@ int marl_dqn_update_n(marl_dqn* q, const marl_traj_view* traj, int32_t batch, in
 int marl_dqn_counters(marl_dqn* q, int64_t* updates, int64_t* last_target_update);
 /* measurement hook (bench.py roofline leg): CUDA-event time of the training-kernel launches between enable=1 and enable=0 */
 int marl_dqn_timing(marl_dqn* q, int32_t enable, float* total_ms, int32_t* count);
+/* after marl_dqn_timing(q, 0, ..): the same window split over the three kernels of the tensor-core training pass, ms3[0..2] =
+ * summed durations of (online forward + TD head, dH1, weight gradients); *count = 0 if the window ran the fused FP32 kernel */
+int marl_dqn_timing_kernels(marl_dqn* q, float* ms3, int32_t* count);
 int marl_dqn_set_counters(marl_dqn* q, int64_t updates, int64_t last_target_update);
 
 /* ------------------------------------------------------------------------------------------------------
