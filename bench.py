@@ -33,7 +33,7 @@ N_AGENTS, OBS_DIM, N_ACTIONS, HIDDEN = 2, 15, 6, 128
 FWD_FLOP_PER_ROW = 2 * (OBS_DIM * HIDDEN + HIDDEN * HIDDEN + HIDDEN * N_ACTIONS)  # 38 144
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload, from the ncu --set full capture summarised in
 # profiles/r1_tc_pipeline.md (cold caches: ncu flushes L2 before every kernel)
-TRAFFIC_NCU = {"tc_dqn_fwd_kernel": None, "tc_dh1_kernel": None, "tc_dw_kernel": None}
+TRAFFIC_NCU = {"tc_dqn_fwd_kernel": 9303552, "tc_dh1_kernel": 3705344, "tc_dw_kernel": 92672512}
 
 
 def parse():
