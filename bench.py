@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient exchange inside the fused reduce + Adam kernel over NVLink peer memory (default), or one NCCL all-reduce per update")
     ap.add_argument("--tc-backward", type=int, default=1, help="1 = three-kernel tcgen05 training pipeline (default), 0 = fused FP32 FFMA training kernel")
     return ap.parse_args()
 
@@ -127,6 +129,8 @@ def workload_config(args, world):
                         f"{upi} updates per iteration of {args.envs} episodes (BASELINE.json configs[1])",
             "envs_per_gpu": args.envs, "batch_size": args.batch, "updates_per_iteration": upi, "buffer_episodes": args.buffer,
             "parallelism": f"dp{world}" if world > 1 else "single", "global_batch": args.batch * world,
+            "collective": (("gradient sum over NVLink peer memory inside the fused reduce + Adam kernel" if args.collective == "peer"
+                            else "one NCCL all-reduce of 155 KB per update") if world > 1 else None),
             "l2": "inputs larger than L2: each update gathers 1024 random episodes from a %.0f MB replay ring" % (args.buffer * 3421 / 1e6)}
 
 
@@ -157,6 +161,8 @@ def run_b200(args):
     env = make_env(args.seed, name=ENV_NAME, time_limit=T, parallel_envs=E, env_gid0=rank * E)
     cfg = Config(dict(optimizer="Adam", lr=3e-4, gamma=0.99, grad_clip=1.0, double_q=True, target_update_interval_or_tau=200, standardise_returns=False))
     model = QNetwork(env.single_observation_space, env.single_action_space, cfg, [128, 128], False, False, True, "cuda", max_batch=B, max_episode_length=T)
+    if world > 1 and args.collective == "peer":
+        model.attach_peers()
     if world > 1:
         dist.broadcast(model.theta, 0)
         model.hard_update()
@@ -177,7 +183,7 @@ def run_b200(args):
 
     def do_updates():
         n_valid = min(state["pos"], args.buffer)
-        if world == 1:
+        if world == 1 or args.collective == "peer":   # peer: the gradient sum of all ranks happens inside the fused reduce + Adam kernel
             model.update_n(rb, B, n_valid, args.seed + 7919 * rank, state["updates"], U)
         else:
             for u in range(U):

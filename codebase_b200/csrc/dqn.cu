@@ -85,6 +85,8 @@ struct marl_dqn {
   float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh1 = nullptr, *tc_rec = nullptr, *tc_x = nullptr;
   bool tgt_image_current = false;
   unsigned long long* grid_barrier = nullptr; unsigned long long grid_epoch = 0;   // arrival counter of the fused reduce + Adam kernel
+  // gradient exchange over peer memory (several ranks, one process per GPU): own buffer + the peers' buffers opened through CUDA IPC
+  XchgParams xchg = {}; float* xbuf = nullptr; void* peer_base[kMaxRanks] = {};
   // online images: valid = a full pack happened and every later change of theta came from adam_kernel (which updates them in place)
   bool image_current = false, bwd_image_current = false;
   int64_t updates = 0, last_target_update = 0;
@@ -145,6 +147,8 @@ int marl_dqn_destroy(marl_dqn* h) {
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
   cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec); cudaFree(h->tc_x); cudaFree(h->grid_barrier);
+  for (int r = 0; r < kMaxRanks; ++r) if (h->peer_base[r] != nullptr && r != h->xchg.rank) cudaIpcCloseMemHandle(h->peer_base[r]);
+  cudaFree(h->xbuf);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return MARL_OK;
@@ -291,7 +295,8 @@ int marl_dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* epis
   AdamParams ap;
   dqn_adam_params(h, loss_out, ap);
   // one kernel for reduce + clip + Adam when its grid fits the GPU in one wave, else the two kernels
-  if (launch_reduce_adam(rp, ap, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) return MARL_OK;
+  if (launch_reduce_adam(rp, ap, &h->xchg, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) return MARL_OK;
+  MARL_REQUIRE(h->xchg.world <= 1, "marl_dqn_update: the peer-memory exchange needs the fused tail kernel (parameter count too large for one wave)");
   if (int rc = launch_grad_reduce(rp, (cudaStream_t)stream)) return rc;
   return launch_adam(ap, (cudaStream_t)stream);
 }
@@ -356,6 +361,50 @@ int marl_dqn_timing_kernels(marl_dqn* h, float* ms3, int32_t* count) {
       ms3[k] += ms;
     }
   }
+  return MARL_OK;
+}
+
+/* ---- gradient exchange over NVLink peer memory (one process per GPU) ---------------------------------------------------------------
+ * marl_dqn_peer_handle: allocates this rank's exchange buffer (2 slots of [n_params + 4] floats + a flag) and writes its 64-byte
+ * cudaIpcMemHandle_t to handle_out; the caller gathers the handles of all ranks (any transport) and passes them, rank-ordered, to
+ * marl_dqn_peer_attach.  From then on marl_dqn_update / marl_dqn_update_n perform the all-rank gradient sum inside the fused
+ * reduce + Adam kernel (every rank must make the same sequence of update calls); the two-call form with an external all-reduce
+ * between marl_dqn_update_grads and marl_dqn_update_apply keeps working. */
+static size_t xbuf_data_bytes(const marl_dqn* h) { return (size_t)2 * kMaxRanks * h->xchg.slot_floats * sizeof(float); }
+
+int marl_dqn_peer_handle(marl_dqn* h, void* handle_out) {
+  MARL_REQUIRE(h != nullptr && handle_out != nullptr, "marl_dqn_peer_handle: NULL argument");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  if (h->xbuf == nullptr) {   // sized for the largest world: [2 parities][kMaxRanks sources][slot] floats + kMaxRanks flags
+    h->xchg.slot_floats = (int)((h->n_params + 4 + 63) / 64 * 64);
+    MARL_CUDA_TRY(cudaMalloc(&h->xbuf, xbuf_data_bytes(h) + 256));
+    MARL_CUDA_TRY(cudaMemset(h->xbuf, 0, xbuf_data_bytes(h) + 256));
+  }
+  cudaIpcMemHandle_t mh;
+  MARL_CUDA_TRY(cudaIpcGetMemHandle(&mh, h->xbuf));
+  memcpy(handle_out, &mh, sizeof(mh));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+  return MARL_OK;
+}
+
+int marl_dqn_peer_attach(marl_dqn* h, int32_t rank, int32_t world, const void* handles) {
+  MARL_REQUIRE(h != nullptr && handles != nullptr, "marl_dqn_peer_attach: NULL argument");
+  MARL_REQUIRE(world >= 2 && world <= kMaxRanks && rank >= 0 && rank < world, "marl_dqn_peer_attach: rank %d / world %d out of range (2..%d ranks)", rank, world, kMaxRanks);
+  MARL_REQUIRE(h->xbuf != nullptr && h->xchg.world <= 1, "marl_dqn_peer_attach: call marl_dqn_peer_handle first, attach once");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  for (int r = 0; r < world; ++r) {
+    void* base = h->xbuf;
+    if (r != rank) {
+      cudaIpcMemHandle_t mh;
+      memcpy(&mh, static_cast<const char*>(handles) + 64 * (size_t)r, sizeof(mh));
+      MARL_CUDA_TRY(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->peer_base[r] = base;
+    h->xchg.peers[r] = static_cast<float*>(base);
+    h->xchg.peer_flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + xbuf_data_bytes(h));
+  }
+  h->xchg.own_flags = h->xchg.peer_flags[rank];
+  h->xchg.rank = rank; h->xchg.world = world; h->xchg.epoch = 0;
   return MARL_OK;
 }
 

@@ -159,7 +159,17 @@ int learner_kernels_init(int in_dim);                       // opt in to > 48 KB
 int launch_mlp_forward(const FwdParams& p, cudaStream_t st);
 int launch_train(const TrainParams& p, int head, cudaStream_t st);
 int launch_grad_reduce(const ReduceParams& p, cudaStream_t st);
-int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st);
+// Gradient exchange over NVLink peer memory (reduce_adam_kernel<true>): every rank owns an exchange buffer
+// [2 parities][world source ranks][slot_floats] floats + [world] 64-bit flags, opened by the other ranks through CUDA IPC.
+constexpr int kMaxRanks = 8;
+struct XchgParams {
+  int world, rank, slot_floats;
+  unsigned long long epoch;                        // number of exchanges so far, this one included
+  float* peers[kMaxRanks];                         // every rank's buffer (own included)
+  unsigned long long* peer_flags[kMaxRanks];       // every rank's flag array (own included): flag[source rank]
+  const unsigned long long* own_flags;             // = peer_flags[rank]
+};
+int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
 template <int KP>

@@ -475,15 +475,53 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Single-GPU tail of an update in ONE kernel: grad_reduce_kernel's deterministic partial sums, a grid-wide barrier, then
-// adam_kernel's clip + Adam step on the gradient each thread still holds in a register.  256 parameters x 4 CTA-slices per block,
-// every load of a thread in flight at once, one wave (the launcher guarantees that all blocks are co-resident, which the hand-made
-// barrier needs; `barrier` counts block arrivals across launches and is never reset, `target` is its value once this launch has
-// fully arrived).  grad[] and the statistics are still published: metrics and the two-call API read them.
+// The tail of an update in ONE kernel: grad_reduce_kernel's deterministic partial sums, (several ranks: the gradient exchange over
+// NVLink peer memory,) a grid-wide barrier, then adam_kernel's clip + Adam step on the gradient each thread still holds in a register.
+// 256 parameters x 4 CTA-slices per block, every load of a thread in flight at once, one wave (the launcher guarantees that all blocks
+// are co-resident, which the hand-made barrier needs; `barrier` counts block arrivals across launches and is never reset, `target` is
+// its value once this launch has fully arrived -- a second arrival round follows when XCHG).  grad[] and the statistics are still
+// published: metrics and the two-call API read them.
+//
+// XCHG (one process per GPU, buffers opened through CUDA IPC): a push exchange.  Every rank's buffer holds, per epoch parity, one copy
+// of [gradient | 4 statistics] PER SOURCE RANK plus one flag per source rank.  A rank stores its local sums into its own copy on every
+// rank (posted remote stores over NVLink), makes them visible system-wide, and writes `epoch` into its flag on every rank; a block
+// then polls only LOCAL flags and reads only LOCAL memory, adding the ranks' values of its parameter in rank order -- the same order on
+// every rank, so the replicated parameters stay bit-identical without a second exchange.  Two parities suffice: a rank pushes epoch
+// e + 1 only after its kernel of epoch e has completed (it has read everything of epoch e), and nobody pushes parity e & 1 again before
+// having seen e + 1 from everybody.
 constexpr int kFusedParams = 256, kFusedSlices = 4;
-__global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kernel(ReduceParams rp, AdamParams ap, unsigned long long* barrier, unsigned long long target) {
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {   // peer memory: never from a stale L1 line
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+// block-wide arrival at the grid barrier; returns once `target` arrivals have been counted (thread 0 spins, the block waits on it)
+__device__ __forceinline__ void grid_barrier(unsigned long long* barrier, unsigned long long target, bool system_scope) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (system_scope) __threadfence_system(); else __threadfence();
+    atomicAdd(barrier, 1ULL);
+    while (*reinterpret_cast<volatile unsigned long long*>(barrier) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <bool XCHG>
+__global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kernel(ReduceParams rp, AdamParams ap, XchgParams xp, unsigned long long* barrier,
+                                                                                  unsigned long long target) {
   __shared__ float part[kFusedSlices][kFusedParams];
   __shared__ float red[kFusedParams * kFusedSlices];
+  __shared__ float stats_sh[4];
   const int t = threadIdx.x, lane = t & (kFusedParams - 1), q = t / kFusedParams;
   const int i = blockIdx.x * kFusedParams + lane, n = rp.n_nets * rp.P;
   pdl_wait();
@@ -503,11 +541,14 @@ __global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kerne
   part[q][lane] = s;
   __syncthreads();
   float g = 0.f;
+  // this rank's copy inside rank r's buffer: base_r + ((epoch & 1) * world + rank) * slot_floats
+  const size_t push_off = XCHG ? ((size_t)(xp.epoch & 1ULL) * xp.world + xp.rank) * xp.slot_floats : 0;
   if (q == 0) {
     g = (part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]);
-    if (i < n) rp.grad[i] = g; else g = 0.f;
+    if (i >= n) g = 0.f;
+    else if (XCHG) { for (int r = 0; r < xp.world; ++r) xp.peers[r][push_off + i] = g; }   // local sums -> every rank (own included)
+    else rp.grad[i] = g;
   }
-  red[t] = g * g;   // zero outside slice 0
   // the four loss statistics: one warp each of block 0, fixed order
   if (blockIdx.x == 0 && t >= kFusedParams && t < kFusedParams + 128) {
     const int which = (t - kFusedParams) >> 5, l = t & 31;
@@ -515,25 +556,45 @@ __global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kerne
     for (int c = l; c < rp.n_loss_parts; c += 32) x += rp.loss_part[4 * c + which];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);
-    if (l == 0) rp.stats[which] = (rp.stats_accumulate ? rp.stats[which] : 0.f) + x;
+    if (l == 0) {
+      x += rp.stats_accumulate ? rp.stats[which] : 0.f;
+      if (XCHG) { for (int r = 0; r < xp.world; ++r) xp.peers[r][push_off + n + which] = x; } else rp.stats[which] = x;
+    }
   }
+  if (XCHG) {
+    // ---- exchange: local sums visible system-wide -> publish the epoch -> wait for every peer -> sum in rank order -----------------
+    grid_barrier(barrier, target - gridDim.x, true);   // every block's pushes are ordered before the flags (system-scope fences)
+    if (blockIdx.x == 0 && t < xp.world) st_release_sys(xp.peer_flags[t] + xp.rank, xp.epoch);   // my flag on rank t
+    if (t < xp.world) { while (ld_acquire_sys(xp.own_flags + t) < xp.epoch) {} }                  // local polling only
+    __syncthreads();
+    const float* mine = xp.peers[xp.rank] + (size_t)(xp.epoch & 1ULL) * xp.world * xp.slot_floats;
+    if (q == 0 && i < n) {
+      g = 0.f;
+      for (int r = 0; r < xp.world; ++r) g += ld_relaxed_sys(mine + (size_t)r * xp.slot_floats + i);
+      rp.grad[i] = g;
+    }
+    if (t < 4) {
+      float x = 0.f;
+      for (int r = 0; r < xp.world; ++r) x += ld_relaxed_sys(mine + (size_t)r * xp.slot_floats + n + t);
+      stats_sh[t] = x;
+      if (blockIdx.x == 0) rp.stats[t] = x;
+    }
+  }
+  red[t] = g * g;   // zero outside slice 0
   __syncthreads();
   for (int k = kFusedParams / 2; k > 0; k >>= 1) { if (t < k) red[t] += red[t + k]; __syncthreads(); }
-  if (t == 0) {
-    rp.sumsq_part[blockIdx.x] = red[0];
-    __threadfence();                       // this block's sum of squares (and block 0's statistics) before its arrival
-    atomicAdd(barrier, 1ULL);
-    while (*reinterpret_cast<volatile unsigned long long*>(barrier) < target) {}
-    __threadfence();
-  }
-  __syncthreads();
+  if (t == 0) rp.sumsq_part[blockIdx.x] = red[0];
+  grid_barrier(barrier, target, false);   // every block's sum of squares (and block 0's statistics) are visible after it
   // ---- every block: global norm from the per-block sums (fixed order), clip coefficient ------------------------------------
   float x = 0.f;
   for (int k = t; k < (int)gridDim.x; k += kFusedParams * kFusedSlices) x += __ldcg(rp.sumsq_part + k);
   red[t] = x;
   __syncthreads();
   for (int k = kFusedParams * kFusedSlices / 2; k > 0; k >>= 1) { if (t < k) red[t] += red[t + k]; __syncthreads(); }
-  const float fill = __ldcg(ap.grad + ap.n + 1), inv_fill = 1.f / fill;
+  float st4[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st4[k] = XCHG ? stats_sh[k] : __ldcg(ap.grad + ap.n + k);
+  const float fill = st4[1], inv_fill = 1.f / fill;
   const float norm = sqrtf(red[0]) * inv_fill;
   float clip = 1.f;
   if (ap.grad_clip > 0.f) clip = fminf(ap.grad_clip / (norm + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
@@ -556,8 +617,8 @@ __global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kerne
     }
   }
   if (blockIdx.x == 0 && t == 0 && ap.loss_out) {
-    ap.loss_out[0] = __ldcg(ap.grad + ap.n) * inv_fill; ap.loss_out[1] = norm; ap.loss_out[2] = __ldcg(ap.grad + ap.n + 2) * inv_fill;
-    ap.loss_out[3] = __ldcg(ap.grad + ap.n + 3) * inv_fill; ap.loss_out[4] = fill; ap.loss_out[5] = 0.f;
+    ap.loss_out[0] = st4[0] * inv_fill; ap.loss_out[1] = norm; ap.loss_out[2] = st4[2] * inv_fill;
+    ap.loss_out[3] = st4[3] * inv_fill; ap.loss_out[4] = fill; ap.loss_out[5] = 0.f;
   }
 }
 
@@ -607,11 +668,20 @@ int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
 }
 
 // Fused tail; returns MARL_EINVAL without launching when the grid could not be co-resident (the caller then uses the two kernels).
-int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st) {
+// xp: NULL or world == 1 -> single GPU; else the exchange over peer memory (xp->epoch is advanced here).
+int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st) {
   const int n = rp.n_nets * rp.P, grid = (n + kFusedParams - 1) / kFusedParams;
   if (grid > 2 * n_sm || ap.n != n) return MARL_EINVAL;   // two 1024-thread blocks fit on an SM
-  *epoch += (unsigned long long)grid;
-  MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel, dim3(grid), dim3(kFusedParams * kFusedSlices), 0, st, rp, ap, barrier, *epoch));
+  XchgParams x; memset(&x, 0, sizeof(x));
+  if (xp != nullptr && xp->world > 1) {
+    xp->epoch += 1;
+    x = *xp;
+    *epoch += 2ULL * (unsigned long long)grid;               // two arrival rounds
+    MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel<true>, dim3(grid), dim3(kFusedParams * kFusedSlices), 0, st, rp, ap, x, barrier, *epoch));
+  } else {
+    *epoch += (unsigned long long)grid;
+    MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel<false>, dim3(grid), dim3(kFusedParams * kFusedSlices), 0, st, rp, ap, x, barrier, *epoch));
+  }
   return MARL_OK;
 }
 

@@ -188,6 +188,20 @@ class QNetwork:
         nat.check(self._lib.marl_dqn_timing(self._h, C.c_int32(int(enable)), C.byref(ms), C.byref(n)), "marl_dqn_timing")
         return float(ms.value), int(n.value)
 
+    def attach_peers(self, group=None):
+        """Several ranks, one process per GPU: exchange CUDA IPC handles through torch.distributed and let `update` / `update_n` sum
+        the gradients of all ranks over NVLink peer memory inside the fused reduce + Adam kernel (no all-reduce call per update)."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = (C.c_ubyte * 64)()
+        nat.check(self._lib.marl_dqn_peer_handle(self._h, mine), "marl_dqn_peer_handle")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        blob = b"".join(handles)
+        nat.check(self._lib.marl_dqn_peer_attach(self._h, C.c_int32(rank), C.c_int32(world), blob), "marl_dqn_peer_attach")
+        dist.barrier(group)
+
     def timing_kernels(self):
         """After timing(False): (ms of online forward + TD head, ms of dH1, ms of weight gradients), launches -- tensor-core pass only."""
         ms3, n = (C.c_float * 3)(), C.c_int32()

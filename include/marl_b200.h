@@ -196,6 +196,13 @@ int marl_dqn_update(marl_dqn* q, const marl_traj_view* traj, const int32_t* epis
 int marl_dqn_update_n(marl_dqn* q, const marl_traj_view* traj, int32_t batch, int32_t n_valid, uint64_t seed,
                       uint64_t first_update_idx, int32_t n_updates, float* loss_out, void* stream);
 int marl_dqn_counters(marl_dqn* q, int64_t* updates, int64_t* last_target_update);
+/* Multi-GPU (one process per GPU on one NVLink node; replaces the torch.distributed all-reduce a data-parallel port of
+ * dqn/train.py would add between loss.backward() and optimiser.step()): marl_dqn_peer_handle allocates this rank's exchange buffer
+ * and writes its 64-byte CUDA IPC handle; the caller gathers all ranks' handles (rank-ordered, 64 bytes each) and passes them to
+ * marl_dqn_peer_attach.  Afterwards marl_dqn_update / marl_dqn_update_n sum the gradients of all ranks over peer memory inside the
+ * fused reduce + Adam kernel (identical parameters on every rank, no NCCL call); every rank must issue the same update calls. */
+int marl_dqn_peer_handle(marl_dqn* q, void* handle_out64);
+int marl_dqn_peer_attach(marl_dqn* q, int32_t rank, int32_t world, const void* handles);
 /* measurement hook (bench.py roofline leg): CUDA-event time of the training-kernel launches between enable=1 and enable=0 */
 int marl_dqn_timing(marl_dqn* q, int32_t enable, float* total_ms, int32_t* count);
 /* after marl_dqn_timing(q, 0, ..): the same window split over the three kernels of the tensor-core training pass, ms3[0..2] =
