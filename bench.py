@@ -162,7 +162,15 @@ def run_b200(args):
     cfg = Config(dict(optimizer="Adam", lr=3e-4, gamma=0.99, grad_clip=1.0, double_q=True, target_update_interval_or_tau=200, standardise_returns=False))
     model = QNetwork(env.single_observation_space, env.single_action_space, cfg, [128, 128], False, False, True, "cuda", max_batch=B, max_episode_length=T)
     if world > 1 and args.collective == "peer":
-        model.attach_peers()
+        try:
+            model.attach_peers()
+        except Exception as e:  # e.g. no peer access between the GPUs of this box: fall back to the NCCL exchange, and say so
+            print(f"[bench] peer-memory exchange unavailable ({e}); using one NCCL all-reduce per update", file=sys.stderr)
+            args.collective = "nccl"
+        flag = torch.tensor([1 if args.collective == "peer" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # all ranks or none
+        if int(flag.item()) == 0:
+            args.collective = "nccl"
     if world > 1:
         dist.broadcast(model.theta, 0)
         model.hard_update()

@@ -188,6 +188,8 @@ class QNetwork:
         nat.check(self._lib.marl_dqn_timing(self._h, C.c_int32(int(enable)), C.byref(ms), C.byref(n)), "marl_dqn_timing")
         return float(ms.value), int(n.value)
 
+    peers_attached = False
+
     def attach_peers(self, group=None):
         """Several ranks, one process per GPU: exchange CUDA IPC handles through torch.distributed and let `update` / `update_n` sum
         the gradients of all ranks over NVLink peer memory inside the fused reduce + Adam kernel (no all-reduce call per update)."""
@@ -200,6 +202,7 @@ class QNetwork:
         dist.all_gather_object(handles, bytes(mine), group=group)
         blob = b"".join(handles)
         nat.check(self._lib.marl_dqn_peer_attach(self._h, C.c_int32(rank), C.c_int32(world), blob), "marl_dqn_peer_attach")
+        self.peers_attached = True
         dist.barrier(group)
 
     def timing_kernels(self):
