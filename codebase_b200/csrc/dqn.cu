@@ -288,17 +288,29 @@ int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   return launch_adam(ap, (cudaStream_t)stream);
 }
 
-int marl_dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, float* loss_out, void* stream) {
+// one update; `next` (optional): replay indices of the following update, drawn inside the fused tail kernel; *fused_out says whether it was
+static int dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, float* loss_out, void* stream, const SampleParams* next,
+                      bool* fused_out) {
+  if (fused_out) *fused_out = false;
   ReduceParams rp;
   if (int rc = dqn_grads(h, traj, episode_idx, batch, stream, &rp)) return rc;
   h->grads_are_local = true;  // nobody touches grad between the two halves: the clip can use the per-block sums of squares
   AdamParams ap;
   dqn_adam_params(h, loss_out, ap);
   // one kernel for reduce + clip + Adam when its grid fits the GPU in one wave, else the two kernels
-  if (launch_reduce_adam(rp, ap, &h->xchg, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) return MARL_OK;
+  SampleParams sp; memset(&sp, 0, sizeof(sp));
+  if (next != nullptr) sp = *next;
+  if (launch_reduce_adam(rp, ap, &h->xchg, sp, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) {
+    if (fused_out) *fused_out = true;
+    return MARL_OK;
+  }
   MARL_REQUIRE(h->xchg.world <= 1, "marl_dqn_update: the peer-memory exchange needs the fused tail kernel (parameter count too large for one wave)");
   if (int rc = launch_grad_reduce(rp, (cudaStream_t)stream)) return rc;
   return launch_adam(ap, (cudaStream_t)stream);
+}
+
+int marl_dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, float* loss_out, void* stream) {
+  return dqn_update(h, traj, episode_idx, batch, loss_out, stream, nullptr, nullptr);
 }
 
 /* n_updates back-to-back updates with on-device replay sampling: the `rb.sample(); model.update()` pair of
@@ -307,9 +319,14 @@ int marl_dqn_update_n(marl_dqn* h, const marl_traj_view* traj, int32_t batch, in
                       int32_t n_updates, float* loss_out, void* stream) {
   MARL_REQUIRE(h && traj && n_updates >= 0, "marl_dqn_update_n: bad argument");
   MARL_REQUIRE(n_valid >= 1 && n_valid <= traj->capacity, "marl_dqn_update_n: n_valid %d out of range", n_valid);
+  bool have_idx = false;   // the previous update's tail kernel already drew this update's indices
   for (int u = 0; u < n_updates; ++u) {
-    if (int rc = marl_replay_sample(seed, first_update_idx + (uint64_t)u, batch, n_valid, h->idx, stream)) return rc;
-    if (int rc = marl_dqn_update(h, traj, h->idx, batch, loss_out, stream)) return rc;
+    if (!have_idx)
+      if (int rc = marl_replay_sample(seed, first_update_idx + (uint64_t)u, batch, n_valid, h->idx, stream)) return rc;
+    SampleParams next; next.seed = seed; next.update_idx = first_update_idx + (uint64_t)u + 1; next.batch = batch; next.n_valid = n_valid; next.idx = h->idx;
+    bool fused = false;
+    if (int rc = dqn_update(h, traj, h->idx, batch, loss_out, stream, u + 1 < n_updates ? &next : nullptr, &fused)) return rc;
+    have_idx = fused && u + 1 < n_updates;
   }
   return MARL_OK;
 }

@@ -169,7 +169,10 @@ struct XchgParams {
   unsigned long long* peer_flags[kMaxRanks];       // every rank's flag array (own included): flag[source rank]
   const unsigned long long* own_flags;             // = peer_flags[rank]
 };
-int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st);
+// replay indices for the next update, drawn by the fused tail kernel (idx == NULL: none); same stream as replay_sample_kernel
+struct SampleParams { uint64_t seed, update_idx; int batch, n_valid; int32_t* idx; };
+int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, const SampleParams& sp, unsigned long long* barrier, unsigned long long* epoch,
+                       int n_sm, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
 
 template <int KP>

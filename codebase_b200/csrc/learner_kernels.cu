@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
 // every rank, so the replicated parameters stay bit-identical without a second exchange.  Two parities suffice: a rank pushes epoch
 // e + 1 only after its kernel of epoch e has completed (it has read everything of epoch e), and nobody pushes parity e & 1 again before
 // having seen e + 1 from everybody.
-constexpr int kFusedParams = 256, kFusedSlices = 4;
+constexpr int kFusedMaxParams = 512, kFusedMaxSlices = 4, kFusedThreads = 1024;   // block shape is chosen at launch: pb parameters x ns slices
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -517,13 +517,14 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* barrier, unsign
 }
 
 template <bool XCHG>
-__global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kernel(ReduceParams rp, AdamParams ap, XchgParams xp, unsigned long long* barrier,
-                                                                                  unsigned long long target) {
-  __shared__ float part[kFusedSlices][kFusedParams];
-  __shared__ float red[kFusedParams * kFusedSlices];
+__global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams rp, AdamParams ap, XchgParams xp, SampleParams sp, int pb, int ns,
+                                                                    unsigned long long* barrier, unsigned long long target) {
+  __shared__ float part[kFusedMaxSlices][kFusedMaxParams];
+  __shared__ float red[32];
   __shared__ float stats_sh[4];
-  const int t = threadIdx.x, lane = t & (kFusedParams - 1), q = t / kFusedParams;
-  const int i = blockIdx.x * kFusedParams + lane, n = rp.n_nets * rp.P;
+  // pb parameters (a multiple of 32) x ns CTA-slices per block, blockDim.x = pb * ns
+  const int t = threadIdx.x, q = t / pb, lane = t - q * pb;
+  const int i = blockIdx.x * pb + lane, n = rp.n_nets * rp.P;
   pdl_wait();
   pdl_launch_dependents();
   float s = 0.f;
@@ -531,27 +532,34 @@ __global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kerne
     const int net = i / rp.P, j = i - net * rp.P;
     const int c0 = rp.cta_begin[net], c1 = rp.cta_begin[net + 1];
     const float* base = rp.scratch + j;
-    for (int cb = c0 + q; cb < c1; cb += 10 * kFusedSlices) {
-      float v[10];
+    for (int cb = c0 + q; cb < c1; cb += 20 * ns) {   // 74 CTAs per network / 3 slices: two rounds of up to 20 loads in flight
+      float v[20];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) { const int c = cb + k * kFusedSlices; v[k] = c < c1 ? base[(size_t)c * rp.scratch_pitch] : 0.f; }
-      s += (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) + (v[8] + v[9]);
+      for (int k = 0; k < 20; ++k) { const int c = cb + k * ns; v[k] = c < c1 ? base[(size_t)c * rp.scratch_pitch] : 0.f; }
+      float u[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) u[k] = (v[4 * k] + v[4 * k + 1]) + (v[4 * k + 2] + v[4 * k + 3]);
+      s += ((u[0] + u[1]) + (u[2] + u[3])) + u[4];
     }
   }
+  // this thread's optimiser state: the loads fly under the reductions and barriers below
+  float m_i = 0.f, v_i = 0.f, th_i = 0.f;
+  if (q == 0 && i < ap.n) { m_i = ap.m[i]; v_i = ap.v[i]; th_i = ap.theta[i]; }
   part[q][lane] = s;
   __syncthreads();
   float g = 0.f;
   // this rank's copy inside rank r's buffer: base_r + ((epoch & 1) * world + rank) * slot_floats
   const size_t push_off = XCHG ? ((size_t)(xp.epoch & 1ULL) * xp.world + xp.rank) * xp.slot_floats : 0;
   if (q == 0) {
-    g = (part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]);
+    g = part[0][lane];
+    for (int k = 1; k < ns; ++k) g += part[k][lane];
     if (i >= n) g = 0.f;
     else if (XCHG) { for (int r = 0; r < xp.world; ++r) xp.peers[r][push_off + i] = g; }   // local sums -> every rank (own included)
     else rp.grad[i] = g;
   }
   // the four loss statistics: one warp each of block 0, fixed order
-  if (blockIdx.x == 0 && t >= kFusedParams && t < kFusedParams + 128) {
-    const int which = (t - kFusedParams) >> 5, l = t & 31;
+  if (blockIdx.x == 0 && t >= pb && t < pb + 128) {   // (the launcher guarantees ns >= 2 and pb >= 128)
+    const int which = (t - pb) >> 5, l = t & 31;
     float x = 0.f;
     for (int c = l; c < rp.n_loss_parts; c += 32) x += rp.loss_part[4 * c + which];
 #pragma unroll
@@ -580,17 +588,29 @@ __global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kerne
       if (blockIdx.x == 0) rp.stats[t] = x;
     }
   }
-  red[t] = g * g;   // zero outside slice 0
+  // block sum of squares: slice 0 holds the gradients (pb / 32 warps) -> shuffle tree per warp, then the partials in order
+  if (q == 0) {
+    float sq = g * g;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, off);
+    if ((t & 31) == 0) red[t >> 5] = sq;
+  }
   __syncthreads();
-  for (int k = kFusedParams / 2; k > 0; k >>= 1) { if (t < k) red[t] += red[t + k]; __syncthreads(); }
-  if (t == 0) rp.sumsq_part[blockIdx.x] = red[0];
+  if (t == 0) {
+    float x = red[0];
+    for (int k = 1; k < pb / 32; ++k) x += red[k];
+    rp.sumsq_part[blockIdx.x] = x;
+  }
   grid_barrier(barrier, target, false);   // every block's sum of squares (and block 0's statistics) are visible after it
-  // ---- every block: global norm from the per-block sums (fixed order), clip coefficient ------------------------------------
-  float x = 0.f;
-  for (int k = t; k < (int)gridDim.x; k += kFusedParams * kFusedSlices) x += __ldcg(rp.sumsq_part + k);
-  red[t] = x;
+  // ---- every block: global norm from the per-block sums (fixed order: lane k adds blocks k, k + 32, ..., then a shuffle tree) ----
+  if (t < 32) {
+    float x = 0.f;
+    for (int k = t; k < (int)gridDim.x; k += 32) x += __ldcg(rp.sumsq_part + k);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);
+    if (t == 0) red[0] = x;
+  }
   __syncthreads();
-  for (int k = kFusedParams * kFusedSlices / 2; k > 0; k >>= 1) { if (t < k) red[t] += red[t + k]; __syncthreads(); }
   float st4[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) st4[k] = XCHG ? stats_sh[k] : __ldcg(ap.grad + ap.n + k);
@@ -600,7 +620,7 @@ __global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kerne
   if (ap.grad_clip > 0.f) clip = fminf(ap.grad_clip / (norm + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
   if (q == 0 && i < ap.n) {
     const float gg = g * inv_fill * clip;
-    float m = ap.m[i], v = ap.v[i], th = ap.theta[i];
+    float m = m_i, v = v_i, th = th_i;
     m = m + (gg - m) * (1.f - ap.beta1);                       // exp_avg.lerp_(grad, 1 - beta1)
     v = v * ap.beta2 + gg * gg * (1.f - ap.beta2);             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(v) / ap.bc2_sqrt + ap.eps;
@@ -614,6 +634,14 @@ __global__ void __launch_bounds__(kFusedParams * kFusedSlices) reduce_adam_kerne
     if (j >= 0 && j < ap.tgt_n) {
       if (ap.target_mode == 1) ap.theta_tgt[j] = th;
       else if (ap.target_mode == 2) ap.theta_tgt[j] = (1.f - ap.tau) * ap.theta_tgt[j] + ap.tau * th;
+    }
+  }
+  // replay indices of the NEXT update (marl_dqn_update_n): np.random.randint(0, len(rb), batch) from the Philox stream -- every reader of
+  // the current indices has completed (this kernel runs after the weight-gradient kernel), and the next sample launch is saved
+  if (sp.idx != nullptr) {
+    for (int k = blockIdx.x * (int)blockDim.x + t; k < sp.batch; k += (int)(gridDim.x * blockDim.x)) {
+      const u32x4 b = philox4x32_10((uint32_t)sp.update_idx, (uint32_t)(sp.update_idx >> 32), (uint32_t)(k >> 2), 0u, (uint32_t)sp.seed, (uint32_t)(sp.seed >> 32) ^ kTagSample);
+      sp.idx[k] = (int32_t)bounded(pick(b, k & 3), (uint32_t)sp.n_valid);
     }
   }
   if (blockIdx.x == 0 && t == 0 && ap.loss_out) {
@@ -667,20 +695,39 @@ int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
   return MARL_OK;
 }
 
-// Fused tail; returns MARL_EINVAL without launching when the grid could not be co-resident (the caller then uses the two kernels).
+// Fused tail; returns MARL_EINVAL without launching when no co-resident grid covers the parameters (the caller then uses the two
+// kernels).  The hand-made grid barrier needs every block resident at once, so the block shape follows from the device: capacity =
+// SMs x (blocks of 1024 threads per SM, from the occupancy API: 1 at this kernel's register count), pb = parameters per block =
+// ceil(n / capacity) rounded up to a warp multiple, ns = slices = 1024 / pb.
 // xp: NULL or world == 1 -> single GPU; else the exchange over peer memory (xp->epoch is advanced here).
-int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, unsigned long long* barrier, unsigned long long* epoch, int n_sm, cudaStream_t st) {
-  const int n = rp.n_nets * rp.P, grid = (n + kFusedParams - 1) / kFusedParams;
-  if (grid > 2 * n_sm || ap.n != n) return MARL_EINVAL;   // two 1024-thread blocks fit on an SM
+int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, const SampleParams& sp, unsigned long long* barrier, unsigned long long* epoch,
+                       int n_sm, cudaStream_t st) {
+  const bool xchg = xp != nullptr && xp->world > 1;
+  static int occ[2] = {0, 0};
+  if (occ[xchg] == 0) {
+    int o = 0;
+    if (xchg) MARL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_adam_kernel<true>, kFusedThreads, 0));
+    else MARL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_adam_kernel<false>, kFusedThreads, 0));
+    occ[xchg] = o > 0 ? o : -1;
+  }
+  const int n = rp.n_nets * rp.P;
+  if (occ[xchg] < 1 || ap.n != n) return MARL_EINVAL;
+  const int capacity = n_sm * occ[xchg];
+  const int pb = ((n + capacity - 1) / capacity + 31) / 32 * 32;
+  if (pb < 128 || pb > kFusedMaxParams) return MARL_EINVAL;
+  int ns = kFusedThreads / pb;
+  if (ns > kFusedMaxSlices) ns = kFusedMaxSlices;
+  if (ns < 2) return MARL_EINVAL;
+  const int grid = (n + pb - 1) / pb;   // <= capacity by construction
   XchgParams x; memset(&x, 0, sizeof(x));
-  if (xp != nullptr && xp->world > 1) {
+  if (xchg) {
     xp->epoch += 1;
     x = *xp;
     *epoch += 2ULL * (unsigned long long)grid;               // two arrival rounds
-    MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel<true>, dim3(grid), dim3(kFusedParams * kFusedSlices), 0, st, rp, ap, x, barrier, *epoch));
+    MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel<true>, dim3(grid), dim3(pb * ns), 0, st, rp, ap, x, sp, pb, ns, barrier, *epoch));
   } else {
     *epoch += (unsigned long long)grid;
-    MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel<false>, dim3(grid), dim3(kFusedParams * kFusedSlices), 0, st, rp, ap, x, barrier, *epoch));
+    MARL_CUDA_TRY(launch_pdl(reduce_adam_kernel<false>, dim3(grid), dim3(pb * ns), 0, st, rp, ap, x, sp, pb, ns, barrier, *epoch));
   }
   return MARL_OK;
 }
