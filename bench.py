@@ -323,7 +323,9 @@ def run_b200(args):
                             "frac": (train_bytes / train_avg_s / 1e9 / hbm_peak) if train_n else None, "bytes_per_launch": train_bytes,
                             "note": "the fused learner is compute-bound (~1 750 FLOP/B, SURVEY F7): the HBM fraction is small by construction"},
                     "bf16_tensor_peak_tflops": peaks.get("bf16_tflops_sustained")}
-    launches_per_step = 1 + 2 * T + U * (6 if kernel_n else 4)   # reset, per env step (forward, env), per update (sample, target forward, 3-kernel pass | fused kernel, reduce + Adam)
+    # reset; per env step: forward, env; per update: target forward, 3-kernel pass | fused FP32 kernel, reduce + Adam (which also draws the next
+    # update's replay indices); one sample kernel per iteration
+    launches_per_step = 1 + 2 * T + U * (5 if kernel_n else 3) + 1
     line = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
