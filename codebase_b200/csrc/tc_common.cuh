@@ -7,7 +7,6 @@
 namespace marl {
 
 
-constexpr int kTcThreads = 128;   // row-per-lane warps (one per TMEM lane quarter)
 constexpr int kTrThreads = 512;   // 16 warps: lane quarter x column quarter
 constexpr int kPanelBytes = kHidden * 128;         // 128 rows x 32 floats
 constexpr int kHeadRows = 16;                      // head GEMM uses N = 16 (minimum for M = 128)

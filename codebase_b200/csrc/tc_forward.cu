@@ -3,10 +3,11 @@
 // Same contract as mlp_forward_kernel (model.act's network pass, the target-network / target-critic pass of the
 // learners; marlbase/dqn/model.py:99,132-134, marlbase/ac/model.py:148-149,190-193) but the three GEMMs of each 128-row
 // tile run on the 5th-generation tensor cores:
-//   * activations never touch shared memory: thread r owns row r = TMEM lane r; the A operand of every layer is written
-//     with tcgen05.st, the accumulator is read back with tcgen05.ld, bias + ReLU happen in registers;
+//   * activations never touch shared memory: row r of a tile = TMEM lane r, 16 warps each own a lane quarter x column quarter;
+//     the A operand of every layer is written with tcgen05.st, the accumulator is read back with tcgen05.ld, bias + ReLU
+//     happen in registers;
 //   * weights are the B operand, resident in shared memory as a pre-packed image (K-major, 128-byte swizzle, one
-//     16-KB panel per 32 input features) built once per parameter change by pack_weights_kernel;
+//     16-KB panel per 32 input features) built by pack_weights_kernel and kept current by the optimiser step (pack_param);
 //   * FP32 parity (<= 1e-5) is kept with the error-compensated 3xTF32 split: every operand is stored as
 //     hi = tf32(x) and lo = tf32(x - hi) and each product is accumulated as lo*hi + hi*lo + hi*hi in the FP32 TMEM
 //     accumulator (measured 4e-7 relative on a 128x128x128 product, tools/tc_probe.cu).
