@@ -174,6 +174,7 @@ class A2CNetwork:
         if getattr(self, "_h", None):
             self._lib.marl_a2c_destroy(self._h)
             self._h = None
+            self.theta = self.theta_tgt = self.adam_m = self.adam_v = self.grad = None  # views of freed library memory
 
     def __del__(self):
         try:

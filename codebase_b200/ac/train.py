@@ -33,7 +33,9 @@ class Collector:
 
     def collect(self):
         env, b = self.env, self.batch
-        b.filled.zero_(); b.done.zero_()  # fresh batch_* tensors every call (ac/train.py:36-52)
+        # fresh, all-zero batch_* tensors on every call (ac/train.py:36-52): compute_nstep_returns never looks at `filled`, so rows after an
+        # early episode end must read as reward 0 / zero observation, not as the previous batch's longer episode in the same slot
+        b.obs.zero_(); b.act.zero_(); b.rew.zero_(); b.filled.zero_(); b.done.zero_()
         env.reset(traj=b, slot0=0)
         for _ in range(self.T):
             self.model.logits(env.obs, out=self.logits)
@@ -44,6 +46,9 @@ class Collector:
 def main(envs, eval_env, logger, time_limit, **cfg):
     cfg = Config(cfg)
     P = envs.num_envs
+    from ..dqn.train import check_iteration_budget
+
+    check_iteration_budget(P, time_limit, cfg.total_steps, cfg.eval_interval)
     model = instantiate(cfg.model, envs.single_observation_space, envs.single_action_space, cfg, max_envs=P, max_episode_length=time_limit)
     logger.watch(model)
     collector = Collector(envs, model, time_limit, cfg.use_proper_termination)

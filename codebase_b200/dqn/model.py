@@ -9,6 +9,7 @@ owner of device buffers.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import random
 import math
 from collections import OrderedDict
 
@@ -143,8 +144,10 @@ class QNetwork:
         obs = torch.as_tensor(np.stack([np.asarray(i, np.float32) for i in inputs], 0), device=self.device)
         obs = obs.view(self.n_agents, -1, self.in_dim).transpose(0, 1).contiguous()
         q = self.q_values(obs)
-        if epsilon > float(torch.rand((), device="cpu")):
-            actions = torch.randint(0, self.n_actions, (obs.shape[0], self.n_agents))
+        # the reference's stream: ONE `random.random()` per call decides the joint exploration (dqn/model.py:105), the random joint
+        # action comes from Python's `random` as well (seed it with random.seed, as the reference's users do)
+        if epsilon > random.random():
+            actions = torch.tensor([[random.randrange(self.n_actions) for _ in range(self.n_agents)] for _ in range(obs.shape[0])])
         else:
             actions = q.argmax(-1).cpu()
         return (actions[0].tolist() if actions.shape[0] == 1 else actions.T.tolist()), hiddens
@@ -241,6 +244,8 @@ class QNetwork:
         if getattr(self, "_h", None):
             self._lib.marl_dqn_destroy(self._h)
             self._h = None
+            # the views below aliased library-owned device memory that no longer exists
+            self.theta = self.theta_tgt = self.adam_m = self.adam_v = self.grad = None
 
     def __del__(self):
         try:

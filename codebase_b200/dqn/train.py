@@ -44,6 +44,24 @@ def epsilon_schedule(decay_style, decay_over, eps_start, eps_end, exp_decay_rate
     return lambda steps_done: max(eps_end + (eps_start - eps_end) * math.exp(-eps_decay * steps_done), eps_end)
 
 
+def check_iteration_budget(parallel_envs, time_limit, total_steps, eval_interval, eps_decay_over=1.0):
+    """The reference's schedules are written for ONE env (a 25-step episode per iteration).  One vectorised iteration here is up to
+    parallel_envs * time_limit env steps, and epsilon / evaluation / the loop condition are only looked at between iterations: warn when a
+    configuration makes them degenerate (e.g. parallel_envs=4096 with the reference's total_steps=100_000 would be ONE iteration at eps=1)."""
+    import warnings
+
+    per_iter = int(parallel_envs) * int(time_limit)
+    need = 20 * per_iter
+    problems = []
+    if total_steps * eps_decay_over < need:
+        problems.append(f"fewer than 20 iterations inside the epsilon decay (total_steps * eps_decay_over = {int(total_steps * eps_decay_over)})")
+    if eval_interval and eval_interval < per_iter:
+        problems.append(f"eval_interval={eval_interval} is shorter than one iteration")
+    if problems:
+        warnings.warn(f"env.parallel_envs={parallel_envs} x time_limit={time_limit} = {per_iter} env steps per iteration: " + "; ".join(problems) +
+                      f" -- raise algorithm.total_steps to >= {int(need / max(eps_decay_over, 1e-9))} (and the intervals with it) or lower env.parallel_envs", UserWarning, stacklevel=2)
+
+
 class Collector:
     """_collect_trajectory (dqn/train.py:202-237) for every env of a B200VecEnv at once, episode-synchronous: all envs reset,
     step until each one's episode ended (at most `time_limit` steps, finished envs freeze), trajectories land in the ring."""
@@ -71,6 +89,7 @@ def _episode_infos(final_len, final_ret, seconds):
 def main(env, eval_env, logger, time_limit, **cfg):
     cfg = Config(cfg)
     E = env.num_envs
+    check_iteration_budget(E, time_limit, cfg.total_steps, cfg.eval_interval, cfg.eps_decay_over)
     model = instantiate(cfg.model, env.single_observation_space, env.single_action_space, cfg, max_batch=cfg.batch_size, max_episode_length=time_limit)
     logger.watch(model)
     capacity = int(cfg.buffer_size)

@@ -50,10 +50,17 @@ class B200VecEnv:
         return self._obs_tuple(self.native.reset()), {}
 
     def step(self, actions):
-        a = torch.as_tensor(np.asarray(actions), dtype=torch.int32, device=self.native.device)
-        if a.shape == (self.n_agents, self.num_envs):
-            a = a.T
-        a = a.reshape(self.num_envs, self.n_agents).contiguous()
+        """`actions`: the reference's layout only -- one sequence of `parallel_envs` actions per agent, i.e. [N][P]
+        (`actions.squeeze().tolist()` of model.act's i64[N, P, 1], marlbase/ac/train.py:79-81); with one env also the flat
+        per-agent list [N] of the single-env protocol (marlbase/dqn/train.py:217)."""
+        a = np.asarray(actions)
+        if a.ndim == 3 and a.shape[-1] == 1:
+            a = a[..., 0]
+        if a.shape == (self.n_agents,) and self.num_envs == 1:
+            a = a[:, None]
+        if a.shape != (self.n_agents, self.num_envs):
+            raise ValueError(f"actions must have shape (n_agents={self.n_agents}, parallel_envs={self.num_envs}), got {a.shape}")
+        a = torch.as_tensor(a.T.copy(), dtype=torch.int32, device=self.native.device).contiguous()
         obs, rew, done, trunc = self.native.step(a, autoreset=True)
         done_h, trunc_h = done.cpu().numpy().astype(bool), trunc.cpu().numpy().astype(bool)
         info = {}

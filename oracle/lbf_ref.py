@@ -162,7 +162,9 @@ class ForagingRef:
             return self._adjacent_food(row, col) > 0
         return False
 
-    def step(self, actions):
+    def step(self, actions, load_order=None):
+        """`load_order`: optional permutation of the loading players' indices (upstream pops an unordered Python set, SURVEY H2);
+        default = ascending agent index, the order the C oracle and the CUDA kernel fix."""
         c = self.cfg
         self.current_step += 1
         for p in self.players:
@@ -180,6 +182,9 @@ class ForagingRef:
             if len(who) == 1:
                 who[0].position = cell
         pending = set(loading)
+        if load_order is not None:
+            assert sorted(load_order) == loading, "load_order must be a permutation of the loading players"
+            loading = list(load_order)
         for idx in loading:  # ascending agent index; upstream pops an unordered set
             if idx not in pending:
                 continue

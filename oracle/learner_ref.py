@@ -173,7 +173,7 @@ def dqn_update(st: DqnState, batch, hp: DqnHP):
         st.last_target_update = st.updates
     elif tu < 1.0:
         st.theta_tgt.copy_((1 - tu) * st.theta_tgt + tu * st.theta)
-    return dict(loss=float(loss.detach()), grad=raw, grad_norm=float(norm))
+    return dict(loss=float(loss.detach()), grad=raw, grad_norm=float(norm), grad_clipped=grad.detach().clone())
 
 
 def epsilon_schedule(decay_style, decay_over, eps_start, eps_end, exp_decay_rate, total_steps):
@@ -322,4 +322,5 @@ def a2c_update(st: A2CState, batch, hp: A2CHP, step: int):
         st.target.copy_(st.critic)
     elif tu < 1.0:
         st.target.copy_((1 - tu) * st.target + tu * st.critic)
-    return dict(loss=float(loss.detach()), actor_loss=float(actor_loss.detach()), value_loss=float(value_loss.detach()), entropy=float(ent.detach()), grad=raw, returns=returns.detach())
+    return dict(loss=float(loss.detach()), actor_loss=float(actor_loss.detach()), value_loss=float(value_loss.detach()), entropy=float(ent.detach()), grad=raw, returns=returns.detach(),
+                grad_clipped=dict(actor=g_actor.detach().clone(), critic=g_critic.detach().clone()))

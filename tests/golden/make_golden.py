@@ -15,6 +15,24 @@ from oracle import ref_shim  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 N, D, A, T = 2, 15, 6, 25
+# fixed integers: Python's hash() of a str is salted per process, which made the fixtures irreproducible
+SEEDS = {"idqn_indep": 101, "idqn_single_q_polyak_noclip": 202, "idqn_shared": 303, "vdn_indep": 404, "ia2c_indep": 505, "ia2c_shared": 606}
+
+
+def optimizer_state_flat(model, module_name, prefix, n_nets, key):
+    """Adam's exp_avg / exp_avg_sq of one sub-module as a flat vector in the device layout (zeros where a parameter never got a gradient)."""
+    mod = getattr(model, module_name)
+    sd = {}
+    for k, p in mod.named_parameters():
+        st = model.optimizer.state.get(p, {})
+        sd[f"{module_name}.{k}"] = st[key].detach().clone() if key in st else torch.zeros_like(p)
+    return lr.flat_from_state_dict(sd, prefix, n_nets).numpy()
+
+
+def grads_flat(model, module_name, prefix, n_nets):
+    mod = getattr(model, module_name)
+    sd = {f"{module_name}.{k}": (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in mod.named_parameters()}
+    return lr.flat_from_state_dict(sd, prefix, n_nets).numpy()
 
 
 def random_store(rng, cap, n_agents=N):
@@ -38,8 +56,8 @@ def to_ref_batch(mod, store, idx):
 
 def dqn_case(name, cls_name, sharing, n_updates=3, B=8, **cfgkw):
     ref = ref_shim.load()
-    torch.manual_seed(hash(name) % 1000)
-    rng = np.random.default_rng(abs(hash(name)) % 2**32)
+    torch.manual_seed(SEEDS[name])
+    rng = np.random.default_rng(SEEDS[name])
     spaces_o = [ref_shim.Space(shape=(D,)) for _ in range(N)]
     spaces_a = [ref_shim.Space(n=A) for _ in range(N)]
     model = getattr(ref.dqn_model, cls_name)(spaces_o, spaces_a, ref_shim.dqn_cfg(**cfgkw), [128, 128], sharing, False, True, "cpu")
@@ -68,6 +86,10 @@ def dqn_case(name, cls_name, sharing, n_updates=3, B=8, **cfgkw):
             sd_grad = {f"critic.{k}": v for k, v in sd_grad.items()}
             out["grad0"] = lr.flat_from_state_dict(sd_grad, prefix, n_nets).numpy()
         losses.append(model.update(batch)["loss"])
+        if u == 0:  # update() clips in place before optimizer.step(): p.grad now holds what Adam consumed
+            out["grad0_clipped"] = grads_flat(model, "critic", prefix, n_nets)
+    out["adam_m_final"] = optimizer_state_flat(model, "critic", prefix, n_nets, "exp_avg")
+    out["adam_v_final"] = optimizer_state_flat(model, "critic", prefix, n_nets, "exp_avg_sq")
     out["losses"] = np.array(losses, np.float64)
     sd = model.state_dict()
     out["theta_final"] = lr.flat_from_state_dict(sd, prefix, n_nets).numpy()
@@ -78,8 +100,8 @@ def dqn_case(name, cls_name, sharing, n_updates=3, B=8, **cfgkw):
 
 def a2c_case(name, sharing, n_updates=2, P=6, **cfgkw):
     ref = ref_shim.load()
-    torch.manual_seed(abs(hash(name)) % 1000)
-    rng = np.random.default_rng(abs(hash(name)) % 2**32)
+    torch.manual_seed(SEEDS[name])
+    rng = np.random.default_rng(SEEDS[name])
     spaces_o = [ref_shim.Space(shape=(D,)) for _ in range(N)]
     spaces_a = [ref_shim.Space(n=A) for _ in range(N)]
     cfg = ref_shim.a2c_cfg(**cfgkw)
@@ -110,7 +132,13 @@ def a2c_case(name, sharing, n_updates=2, P=6, **cfgkw):
             done = acb.dones.float().unsqueeze(-1).repeat(1, 1, N)
             out["returns0"] = ref.utils.compute_nstep_returns(acb.rewards, done, nv, cfg.n_steps, cfg.gamma).numpy()
         m = model.update(acb, steps[u])
+        if u == 0:
+            out["actor_grad0_clipped"] = grads_flat(model, "actor", f"actor.{kind}", n_nets)
+            out["critic_grad0_clipped"] = grads_flat(model, "critic", f"critic.{kind}", n_nets)
         metrics.append([m["loss"], m["actor_loss"], m["value_loss"], m["entropy"]])
+    for mod in ("actor", "critic"):
+        out[f"{mod}_adam_m_final"] = optimizer_state_flat(model, mod, f"{mod}.{kind}", n_nets, "exp_avg")
+        out[f"{mod}_adam_v_final"] = optimizer_state_flat(model, mod, f"{mod}.{kind}", n_nets, "exp_avg_sq")
     out["metrics"] = np.array(metrics, np.float64)
     out["steps"] = np.array(steps[:n_updates])
     sd = model.state_dict()

@@ -21,6 +21,21 @@ def _close(a, b, rtol=1e-5, atol=1e-5):
     assert np.allclose(a, b, rtol=rtol, atol=atol), float(np.abs(a - b).max())
 
 
+def _close_scaled(a, b, tol=1e-5):
+    """element-wise, relative to the tensor's own scale (Adam's second moment lives at 1e-6 .. 1e-10)"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = max(float(np.abs(b).max()), 1e-30)
+    assert np.abs(a - b).max() <= tol * scale, (float(np.abs(a - b).max()), scale)
+
+
+def _clipped(grad, max_norm):
+    """clip_grad_norm_ on the host, from the device's normalised gradient: what the fused Adam step consumes"""
+    if not max_norm:
+        return grad
+    norm = float(np.sqrt((grad.astype(np.float64) ** 2).sum()))
+    return grad * min(1.0, max_norm / (norm + 1e-6))
+
+
 def _space(shape=None, n=None):
     return types.SimpleNamespace(shape=shape, n=n)
 
@@ -74,11 +89,15 @@ def test_update_matches_reference_golden(name):
             gr = m.grad.cpu().numpy()
             n = m.n_params
             _close(gr[:n] / gr[n + 1], g["grad0"])        # un-normalised sums / filled count == autograd gradient
+            _close_scaled(_clipped(gr[:n] / gr[n + 1], hp.grad_clip), g["grad0_clipped"])   # element-wise, what Adam consumes
             _close(gr[n] / gr[n + 1], g["losses"][0])
             met = m.update_apply()
         else:
             met = m.update_from_store(ts, idx)
         _close(met[0].item(), g["losses"][u])
+    # Adam state element-wise against the reference optimiser's exp_avg / exp_avg_sq: the quantile bound on theta cannot hide a defect here
+    _close_scaled(m.adam_m.cpu().numpy(), g["adam_m_final"])
+    _close_scaled(m.adam_v.cpu().numpy(), g["adam_v_final"])
     d = np.abs(m.theta.cpu().numpy() - g["theta_final"])
     assert np.quantile(d, 0.999) < 1e-5 and d.max() < 2 * hp.lr * len(g["losses"]) + 1e-6, (np.quantile(d, 0.999), d.max())
     dt = np.abs(m.theta_tgt.cpu().numpy() - g["target_final"])
@@ -111,8 +130,10 @@ def test_update_matches_oracle_on_random_batches(mixer, sharing, B, n_agents):
         gr = m.grad.cpu().numpy()
         scale = max(1.0, float(np.abs(want["grad"].numpy()).max()))
         _close(gr[:m.n_params] / gr[m.n_params + 1] / scale, want["grad"].numpy() / scale)
+        _close_scaled(_clipped(gr[:m.n_params] / gr[m.n_params + 1], hp.grad_clip), want["grad_clipped"].numpy())
         met = m.update_apply().cpu().numpy()
         _close(met[0], want["loss"]); _close(met[1], want["grad_norm"], rtol=1e-4)
+        _close_scaled(m.adam_m.cpu().numpy(), st.m.numpy()); _close_scaled(m.adam_v.cpu().numpy(), st.v.numpy())
         d = np.abs(m.theta.cpu().numpy() - st.theta.numpy())
         assert np.quantile(d, 0.999) < 1e-5 and d.max() < 2 * hp.lr * (u + 1) + 1e-6
         # keep the two trajectories glued so that later steps compare like for like

@@ -19,6 +19,13 @@ def _close(a, b, rtol=RT, atol=AT):
     assert np.allclose(a, b, rtol=rtol, atol=atol), float(np.abs(a - b).max())
 
 
+def _close_scaled(a, b, tol=1e-5):
+    """element-wise, relative to the tensor's own scale (Adam's second moment lives at 1e-6 .. 1e-10: a plain atol would hide it)"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = max(float(np.abs(b).max()), 1e-30)
+    assert np.abs(a - b).max() <= tol * scale, (float(np.abs(a - b).max()), scale)
+
+
 def load_dqn_case(name):
     g = np.load(os.path.join(GOLD, f"{name}.npz"))
     hp = lr.DqnHP(lr=float(g["hp"][0]), gamma=float(g["hp"][1]), grad_clip=float(g["hp"][2]), double_q=bool(g["hp"][3]),
@@ -37,6 +44,9 @@ def test_dqn_update_matches_reference_golden(name):
         _close(out["loss"], g["losses"][u])
         if u == 0:
             _close(out["grad"].numpy(), g["grad0"])
+            _close_scaled(out["grad_clipped"].numpy(), g["grad0_clipped"])   # what Adam consumed (after clip_grad_norm_)
+    _close_scaled(st.m.numpy(), g["adam_m_final"])   # element-wise: the loose bound on theta below cannot hide a defect here
+    _close_scaled(st.v.numpy(), g["adam_v_final"])
     # Adam's first steps move every weight by ~lr regardless of |g|: elements whose gradient is rounding noise may
     # flip sign between two float32 summation orders, so compare the bulk tightly and bound the rest by 2*lr per step.
     d = np.abs(st.theta.numpy() - g["theta_final"])
@@ -60,6 +70,11 @@ def test_a2c_update_matches_reference_golden(name):
         _close([out["loss"], out["actor_loss"], out["value_loss"], out["entropy"]], g["metrics"][u])
         if u == 0:
             _close(out["returns"].numpy(), g["returns0"])
+            for k in ("actor", "critic"):
+                _close_scaled(out["grad_clipped"][k].numpy(), g[f"{k}_grad0_clipped"])
+    for k in ("actor", "critic"):
+        _close_scaled(st.m[k].numpy(), g[f"{k}_adam_m_final"])
+        _close_scaled(st.v[k].numpy(), g[f"{k}_adam_v_final"])
     for mine, want in ((st.actor, "actor_final"), (st.critic, "critic_final"), (st.target, "target_final")):
         d = np.abs(mine.numpy() - g[want])
         assert np.quantile(d, 0.999) < 1e-5 and d.max() < 2 * hp.lr * len(g["steps"]) + 1e-6

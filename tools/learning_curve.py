@@ -88,12 +88,43 @@ def gpu_run(seed, E):
     return curve
 
 
+def _set_budget(total, eval_every):
+    global TOTAL, EVAL_EVERY
+    TOTAL, EVAL_EVERY = int(total), int(eval_every)
+
+
+def _cpu_entry(args):
+    seed, total, eval_every = args
+    _set_budget(total, eval_every)
+    return cpu_run(seed)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=8)
     ap.add_argument("--envs", type=int, default=64)
+    ap.add_argument("--total", type=int, default=TOTAL, help="environment-step budget per seed")
+    ap.add_argument("--eval-every", type=int, default=EVAL_EVERY)
+    ap.add_argument("--arm", default="both", choices=["both", "cpu", "gpu"],
+                    help="cpu: only the CPU restatement of the reference loop (runs without a GPU); gpu: only the B200 path")
+    ap.add_argument("--out", default=None, help="also write the JSON document here")
     a = ap.parse_args()
+    _set_budget(a.total, a.eval_every)
     t0 = time.time()
+    if a.arm != "both":
+        if a.arm == "cpu":
+            with mp.get_context("spawn").Pool(a.seeds) as pool:
+                curves = pool.map(_cpu_entry, [(s, a.total, a.eval_every) for s in range(a.seeds)])
+        else:
+            curves = [gpu_run(s, a.envs) for s in range(a.seeds)]
+        doc = {"what": "IDQN Foraging-8x8-2p-3f-v3, batch 128, eval returns (sum over agents, 100 episodes, eps 0.05)", "arm": a.arm, "seeds": a.seeds,
+               "total_steps": a.total, "eval_every": a.eval_every, "b200_envs": a.envs if a.arm == "gpu" else None,
+               "seconds": round(time.time() - t0, 1), "curves": curves}
+        txt = json.dumps(doc, indent=1)
+        if a.out:
+            open(a.out, "w").write(txt)
+        print(txt)
+        sys.exit(0)
     ctx = mp.get_context("spawn")
     pool = ctx.Pool(a.seeds)
     cpu_async = pool.map_async(cpu_run, list(range(a.seeds)))
