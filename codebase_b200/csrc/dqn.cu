@@ -409,6 +409,13 @@ int marl_dqn_peer_attach(marl_dqn* h, int32_t rank, int32_t world, const void* h
   MARL_REQUIRE(world >= 2 && world <= kMaxRanks && rank >= 0 && rank < world, "marl_dqn_peer_attach: rank %d / world %d out of range (2..%d ranks)", rank, world, kMaxRanks);
   MARL_REQUIRE(h->xbuf != nullptr && h->xchg.world <= 1, "marl_dqn_peer_attach: call marl_dqn_peer_handle first, attach once");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
+  {  // the exchange lives inside the fused reduce + Adam kernel: refuse here, before any update mutates counters, when that kernel cannot
+     // cover this parameter count with one co-resident wave (a later fallback to the two-kernel tail would dead-lock the peers' polls)
+    int pb = 0, ns = 0;
+    MARL_REQUIRE(reduce_adam_shape((int)h->n_params, h->n_sm, true, &pb, &ns) == MARL_OK,
+                 "marl_dqn_peer_attach: %lld parameters do not fit the fused reduce + Adam kernel on %d SMs; use the all-reduce between marl_dqn_update_grads and _apply",
+                 (long long)h->n_params, h->n_sm);
+  }
   for (int r = 0; r < world; ++r) {
     void* base = h->xbuf;
     if (r != rank) {
@@ -421,7 +428,21 @@ int marl_dqn_peer_attach(marl_dqn* h, int32_t rank, int32_t world, const void* h
     h->xchg.peer_flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + xbuf_data_bytes(h));
   }
   h->xchg.own_flags = h->xchg.peer_flags[rank];
+  h->xchg.timed_out = reinterpret_cast<int*>(static_cast<char*>(h->peer_base[rank]) + xbuf_data_bytes(h) + 128);   // behind the 8 flags, zeroed with the buffer
   h->xchg.rank = rank; h->xchg.world = world; h->xchg.epoch = 0;
+  return MARL_OK;
+}
+
+/* 0 = healthy.  1 = some update's exchange gave up waiting for a peer's flag (a rank died, skipped an update or fell out of step): every
+ * result since is invalid.  Synchronises the device. */
+int marl_dqn_peer_status(marl_dqn* h, int32_t* timed_out) {
+  MARL_REQUIRE(h != nullptr && timed_out != nullptr, "marl_dqn_peer_status: NULL argument");
+  *timed_out = 0;
+  if (h->xchg.world <= 1) return MARL_OK;
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  int v = 0;
+  MARL_CUDA_TRY(cudaMemcpy(&v, h->xchg.timed_out, sizeof(int), cudaMemcpyDeviceToHost));
+  *timed_out = v;
   return MARL_OK;
 }
 

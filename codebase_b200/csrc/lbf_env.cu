@@ -529,8 +529,11 @@ int marl_lbf_create(const marl_lbf_cfg* cfg, int32_t n_envs, uint64_t seed, uint
 #undef ALLOC0
   const int EPC = (kThreads / 32) * (32 / d.G);
   h->step_smem = (size_t)EPC * d.pitch + (size_t)EPC * d.G * 4 + (size_t)EPC * d.NF * 4 + (size_t)EPC * 16 + (size_t)EPC * d.N * d.D * 4;
-  if (h->step_smem > 48 * 1024) {
+  // the attribute is a per-function, process-wide setting: only ever raise it (a second env with a smaller tile must not lower the limit of the first)
+  static size_t step_smem_limit = 48 * 1024;
+  if (h->step_smem > step_smem_limit) {
     cudaError_t e = cudaFuncSetAttribute(lbf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem);
+    if (e == cudaSuccess) step_smem_limit = h->step_smem;
     if (e != cudaSuccess) { set_error("marl_lbf_create: %zu B of shared memory per CTA not available: %s", h->step_smem, cudaGetErrorString(e)); marl_lbf_destroy(h); return MARL_EINVAL; }
   }
   *out = h;

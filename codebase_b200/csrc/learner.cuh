@@ -168,12 +168,15 @@ struct XchgParams {
   float* peers[kMaxRanks];                         // every rank's buffer (own included)
   unsigned long long* peer_flags[kMaxRanks];       // every rank's flag array (own included): flag[source rank]
   const unsigned long long* own_flags;             // = peer_flags[rank]
+  int* timed_out;                                  // device flag (sticky): a peer's epoch flag did not arrive within the spin bound
 };
 // replay indices for the next update, drawn by the fused tail kernel (idx == NULL: none); same stream as replay_sample_kernel
 struct SampleParams { uint64_t seed, update_idx; int batch, n_valid; int32_t* idx; };
 int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, const SampleParams& sp, unsigned long long* barrier, unsigned long long* epoch,
                        int n_sm, cudaStream_t st);
 int launch_adam(const AdamParams& p, cudaStream_t st);
+// can the fused tail cover n parameters with one co-resident wave on n_sm SMs?  (pb, ns: the block shape it would use)
+int reduce_adam_shape(int n, int n_sm, bool xchg, int* pb, int* ns);
 
 template <int KP>
 constexpr size_t forward_smem_bytes() { return sizeof(float) * (WeightSmem<KP>::kFloats + 2 * kTileRows * kPitchH + kTileRows * kOutPad + 48) + RowMeta::kBytes; }

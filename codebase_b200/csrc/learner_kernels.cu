@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams p) {
 // every rank, so the replicated parameters stay bit-identical without a second exchange.  Two parities suffice: a rank pushes epoch
 // e + 1 only after its kernel of epoch e has completed (it has read everything of epoch e), and nobody pushes parity e & 1 again before
 // having seen e + 1 from everybody.
+constexpr long long kPeerSpinCycles = 20LL * 1000 * 1000 * 1000;   // ~10 s at 2 GHz: far beyond any healthy exchange (~10 us)
 constexpr int kFusedMaxParams = 512, kFusedMaxSlices = 4, kFusedThreads = 1024;   // block shape is chosen at launch: pb parameters x ns slices
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -573,7 +574,12 @@ __global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams
     // ---- exchange: local sums visible system-wide -> publish the epoch -> wait for every peer -> sum in rank order -----------------
     grid_barrier(barrier, target - gridDim.x, true);   // every block's pushes are ordered before the flags (system-scope fences)
     if (blockIdx.x == 0 && t < xp.world) st_release_sys(xp.peer_flags[t] + xp.rank, xp.epoch);   // my flag on rank t
-    if (t < xp.world) { while (ld_acquire_sys(xp.own_flags + t) < xp.epoch) {} }                  // local polling only
+    if (t < xp.world) {   // local polling only; bounded: a rank that died / skipped an update must not hang this GPU for ever
+      const long long t0 = clock64();
+      while (ld_acquire_sys(xp.own_flags + t) < xp.epoch) {
+        if (clock64() - t0 > kPeerSpinCycles) { atomicExch(xp.timed_out, 1); break; }   // sticky; the host raises on it (marl_dqn_peer_status)
+      }
+    }
     __syncthreads();
     const float* mine = xp.peers[xp.rank] + (size_t)(xp.epoch & 1ULL) * xp.world * xp.slot_floats;
     if (q == 0 && i < n) {
@@ -646,7 +652,8 @@ __global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams
   }
   if (blockIdx.x == 0 && t == 0 && ap.loss_out) {
     ap.loss_out[0] = st4[0] * inv_fill; ap.loss_out[1] = norm; ap.loss_out[2] = st4[2] * inv_fill;
-    ap.loss_out[3] = st4[3] * inv_fill; ap.loss_out[4] = fill; ap.loss_out[5] = 0.f;
+    ap.loss_out[3] = st4[3] * inv_fill; ap.loss_out[4] = fill;
+    ap.loss_out[5] = (XCHG && *reinterpret_cast<volatile int*>(xp.timed_out)) ? 1.f : 0.f;   // 1 = the peer exchange timed out: results are invalid
   }
 }
 
@@ -700,9 +707,7 @@ int launch_grad_reduce(const ReduceParams& p, cudaStream_t st) {
 // SMs x (blocks of 1024 threads per SM, from the occupancy API: 1 at this kernel's register count), pb = parameters per block =
 // ceil(n / capacity) rounded up to a warp multiple, ns = slices = 1024 / pb.
 // xp: NULL or world == 1 -> single GPU; else the exchange over peer memory (xp->epoch is advanced here).
-int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, const SampleParams& sp, unsigned long long* barrier, unsigned long long* epoch,
-                       int n_sm, cudaStream_t st) {
-  const bool xchg = xp != nullptr && xp->world > 1;
+int reduce_adam_shape(int n, int n_sm, bool xchg, int* pb_out, int* ns_out) {
   static int occ[2] = {0, 0};
   if (occ[xchg] == 0) {
     int o = 0;
@@ -710,14 +715,23 @@ int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams*
     else MARL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_adam_kernel<false>, kFusedThreads, 0));
     occ[xchg] = o > 0 ? o : -1;
   }
-  const int n = rp.n_nets * rp.P;
-  if (occ[xchg] < 1 || ap.n != n) return MARL_EINVAL;
+  if (occ[xchg] < 1) return MARL_EINVAL;
   const int capacity = n_sm * occ[xchg];
   const int pb = ((n + capacity - 1) / capacity + 31) / 32 * 32;
   if (pb < 128 || pb > kFusedMaxParams) return MARL_EINVAL;
   int ns = kFusedThreads / pb;
   if (ns > kFusedMaxSlices) ns = kFusedMaxSlices;
   if (ns < 2) return MARL_EINVAL;
+  *pb_out = pb; *ns_out = ns;
+  return MARL_OK;
+}
+
+int launch_reduce_adam(const ReduceParams& rp, const AdamParams& ap, XchgParams* xp, const SampleParams& sp, unsigned long long* barrier, unsigned long long* epoch,
+                       int n_sm, cudaStream_t st) {
+  const bool xchg = xp != nullptr && xp->world > 1;
+  const int n = rp.n_nets * rp.P;
+  int pb = 0, ns = 0;
+  if (ap.n != n || reduce_adam_shape(n, n_sm, xchg, &pb, &ns) != MARL_OK) return MARL_EINVAL;
   const int grid = (n + pb - 1) / pb;   // <= capacity by construction
   XchgParams x; memset(&x, 0, sizeof(x));
   if (xchg) {

@@ -130,6 +130,33 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP): one thread moves a contiguous, 16-byte aligned block global -> shared; completion is
+// counted in bytes on an mbarrier (expect_tx by the issuing thread).  The packed weight images are byte-for-byte shared-memory images, so
+// an image (or a slice of it) is one instruction instead of a loop of per-thread cp.async, and the writes arrive through the async proxy,
+// the one the tensor core reads operands through.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// copy bytes [begin, end) of an image to the same offsets of its shared-memory copy, in pieces of at most 32 KB; the caller has armed `bar`
+// with the total byte count of everything it sends to it (mbar_expect_tx, once)
+__device__ __forceinline__ void tma_image_range(uint32_t smem_base, const uint8_t* src, int begin, int end, uint64_t* bar) {
+  for (int o = begin; o < end; o += 32768) tma_bulk_g2s(smem_base + (uint32_t)o, src + o, (uint32_t)min(32768, end - o), bar);
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// the forward image in the order the first tile needs it: bars[0] <- W1 + biases + FP32 W3, bars[1] <- W2, bars[2] <- W3 (one thread)
+__device__ __forceinline__ void tma_forward_image(uint32_t smem_base, const uint8_t* src, uint64_t* bars) {
+  mbar_expect_tx(bars + 0, (uint32_t)(kOffW2Hi + (kImageBytes - kOffB1)));
+  tma_image_range(smem_base, src, kOffW1Hi, kOffW2Hi, bars + 0);
+  tma_image_range(smem_base, src, kOffB1, kImageBytes, bars + 0);
+  mbar_expect_tx(bars + 1, (uint32_t)(kOffW3Hi - kOffW2Hi));
+  tma_image_range(smem_base, src, kOffW2Hi, kOffW3Hi, bars + 1);
+  mbar_expect_tx(bars + 2, (uint32_t)(kOffB1 - kOffW3Hi));
+  tma_image_range(smem_base, src, kOffW3Hi, kOffB1, bars + 2);
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

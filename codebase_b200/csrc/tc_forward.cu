@@ -81,24 +81,12 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (t == 0) mbar_init(bar, 1);
+  if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); mbar_init(bar + 4, 1); fence_mbar_init(); }
   pdl_wait();   // nothing above touches global memory (PDL contract, common.cuh)
   pdl_launch_dependents();
-  {  // the weight image is already in shared-memory layout: asynchronous 16-byte copies in three groups, in the order the first
-     // tile needs them (W1 + biases, W2, W3), so that its first layer does not wait for the whole image
-    const uint8_t* src = images + (size_t)net * kImageBytes;
-    const uint32_t dst = smem_u32(smem);
-    auto copy = [&](int begin, int end) {
-      for (int i = begin / 16 + t; i < end / 16; i += kTrThreads)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
-    };
-    copy(kOffW1Hi, kOffW2Hi); copy(kOffB1, kImageBytes);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    copy(kOffW2Hi, kOffW3Hi);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    copy(kOffW3Hi, kOffB1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  // the weight image is already in shared-memory layout: three TMA bulk copies (cp.async.bulk -> mbarrier, issued by one thread) in the
+  // order the first tile needs them (W1 + biases, W2, W3), so that its first layer does not wait for the whole image
+  if (t == 0) tma_forward_image(smem_u32(smem), images + (size_t)net * kImageBytes, bar + 2);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -154,7 +142,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
       tmem_st8(lane_base + kColALo + 8 * cq, lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (image_groups_pending == 3) { asm volatile("cp.async.wait_group 2;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); image_groups_pending = 2; }
+    if (image_groups_pending == 3) { mbar_wait(bar + 2, 0); image_groups_pending = 2; }   // W1 + biases have landed
     tc_fence_before();
     __syncthreads();
     // ---- layer 1 -------------------------------------------------------------------------------------------------
@@ -190,8 +178,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       if (image_groups_pending == 2 - layer) {   // W2 before the layer-2 MMAs, W3 before the head's
-        if (layer == 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_wait(bar + 3 + layer, 0);
         image_groups_pending = 1 - layer;
       }
       tc_fence_before();

@@ -82,24 +82,12 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (t == 0) mbar_init(bar, 1);
+  if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); mbar_init(bar + 4, 1); fence_mbar_init(); }
   pdl_wait();   // nothing above touches global memory
   pdl_launch_dependents();
-  {
-    const uint8_t* src = p.images + (size_t)net * kImageBytes;
-    const uint32_t dst = smem_u32(smem);
-    // three cp.async groups in the order the first tile needs them: W1 + biases, W2, W3
-    auto copy = [&](int begin, int end) {
-      for (int i = begin / 16 + t; i < end / 16; i += kTrThreads)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
-    };
-    copy(kOffW1Hi, kOffW2Hi); copy(kOffB1, kImageBytes);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    copy(kOffW2Hi, kOffW3Hi);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    copy(kOffW3Hi, kOffB1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  // the weight image is already in shared-memory layout: three TMA bulk copies (cp.async.bulk -> mbarrier, issued by one thread) in the
+  // order the first tile needs them (W1 + biases, W2, W3), so that its first layer does not wait for the whole image
+  if (t == 0) tma_forward_image(smem_u32(smem), p.images + (size_t)net * kImageBytes, bar + 2);
   const float* b1 = reinterpret_cast<const float*>(smem + kOffB1);
   const float* b2 = reinterpret_cast<const float*>(smem + kOffB2);
   const float* b3 = reinterpret_cast<const float*>(smem + kOffB3);
@@ -174,7 +162,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (image_groups_pending == 3) { asm volatile("cp.async.wait_group 2;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); image_groups_pending = 2; }
+    if (image_groups_pending == 3) { mbar_wait(bar + 2, 0); image_groups_pending = 2; }   // W1 + biases have landed
     tc_fence_before();
     __syncthreads();
     if (t == 0) {
@@ -222,8 +210,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
       }
       if (r < nrows) reinterpret_cast<uint32_t*>(p.rec + dst_row * kRowRec)[4 + 4 * layer + cq] = mask;   // ReLU mask of this layer
       if (image_groups_pending == 2 - layer) {   // W2 before the layer-2 MMAs, W3 before the head's
-        if (layer == 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_wait(bar + 3 + layer, 0);
         image_groups_pending = 1 - layer;
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -323,17 +310,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (t == 0) mbar_init(bar, 1);
+  if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 2, 1); fence_mbar_init(); }
   pdl_wait();   // nothing above touches global memory
   pdl_launch_dependents();
-  {
-    const uint8_t* src = p.bwd_images + (size_t)net * kBwdImageBytes;
-    const uint8_t* w3src = p.images + (size_t)net * kImageBytes + kOffW3F;
-    const uint32_t dst = smem_u32(smem);
-    for (int i = t; i < kBwdImageBytes / 16; i += kTrThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
-    for (int i = t; i < kOutPad * kHidden * 4 / 16; i += kTrThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kDh1W3 + 16u * i), "l"(w3src + 16 * (size_t)i) : "memory");
+  if (t == 0) {  // W2^T image + FP32 W3: TMA bulk copies onto one mbarrier
+    mbar_expect_tx(bar + 2, (uint32_t)(kBwdImageBytes + kOutPad * kHidden * 4));
+    tma_image_range(smem_u32(smem), p.bwd_images + (size_t)net * kBwdImageBytes, 0, kBwdImageBytes, bar + 2);
+    tma_bulk_g2s(smem_u32(smem) + kDh1W3, p.images + (size_t)net * kImageBytes + kOffW3F, kOutPad * kHidden * 4, bar + 2);
   }
   // this thread's row record: dLoss/dq[act], act and the two mask words of its 32 columns; fetched one tile ahead
   struct Rec { long long d; float g; int act; uint32_t m1, m2; };
@@ -352,11 +335,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
   Rec cur, nxt;
   fetch(row_begin, cur);
   nxt = cur;
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  mbar_wait(bar + 2, 0);   // images have landed (every thread reads the FP32 W3 rows; the tensor core reads W2^T)
   const uint32_t tmem = *tmem_slot, smem_base = smem_u32(smem), lane_base = tmem + ((uint32_t)(32 * lq) << 16);
   uint32_t parity = 0;
   for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
@@ -453,7 +435,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDwBars);   // [2] chunk buffer staged (512 producer arrivals)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDwBars);   // [2] chunk buffer staged (16 producer-warp arrivals)
   uint64_t* empty = full + 2;                                     // [2] chunk buffer consumed by the tensor core (tcgen05.commit)
   uint64_t* done = full + 4;                                      // every MMA retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 5);
@@ -475,7 +457,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) {
-    mbar_init(full, kDwProducers); mbar_init(full + 1, kDwProducers);
+    mbar_init(full, kDwProducers / 32); mbar_init(full + 1, kDwProducers / 32);   // one arrival per producer warp
     mbar_init(empty, 1); mbar_init(empty + 1, 1); mbar_init(done, 1);
   }
   // constant panels of both buffers: ones column (n = 128) behind H1 hi, zeros behind H1 lo; W3 copy
@@ -564,13 +546,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
       stage(smem, pre0);
       issue_loads(c + 2, pre0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full);   // 16 arrivals per chunk instead of 512 serialised shared-memory atomics
       if (c + 1 < n_chunks) {
         if (c >= 2) mbar_wait(empty + 1, ((c >> 1) - 1) & 1);
         stage(smem + kSEnd, pre1);
         issue_loads(c + 3, pre1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full + 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 1);
       }
     }
   } else {

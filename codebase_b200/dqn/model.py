@@ -208,6 +208,12 @@ class QNetwork:
         self.peers_attached = True
         dist.barrier(group)
 
+    def peer_timed_out(self) -> bool:
+        """True when an in-kernel gradient exchange gave up waiting for a peer (bounded spin): every result since is invalid."""
+        v = C.c_int32()
+        nat.check(self._lib.marl_dqn_peer_status(self._h, C.byref(v)), "marl_dqn_peer_status")
+        return bool(v.value)
+
     def timing_kernels(self):
         """After timing(False): (ms of online forward + TD head, ms of dH1, ms of weight gradients), launches -- tensor-core pass only."""
         ms3, n = (C.c_float * 3)(), C.c_int32()

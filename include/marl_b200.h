@@ -203,6 +203,9 @@ int marl_dqn_counters(marl_dqn* q, int64_t* updates, int64_t* last_target_update
  * fused reduce + Adam kernel (identical parameters on every rank, no NCCL call); every rank must issue the same update calls. */
 int marl_dqn_peer_handle(marl_dqn* q, void* handle_out64);
 int marl_dqn_peer_attach(marl_dqn* q, int32_t rank, int32_t world, const void* handles);
+/* *timed_out = 1 when an update's in-kernel exchange gave up waiting for a peer (bounded spin, ~10 s): results since are invalid.
+ * The same flag is mirrored in loss_out[5] of every update.  Synchronises the device. */
+int marl_dqn_peer_status(marl_dqn* q, int32_t* timed_out);
 /* measurement hook (bench.py roofline leg): CUDA-event time of the training-kernel launches between enable=1 and enable=0 */
 int marl_dqn_timing(marl_dqn* q, int32_t enable, float* total_ms, int32_t* count);
 /* after marl_dqn_timing(q, 0, ..): the same window split over the three kernels of the tensor-core training pass, ms3[0..2] =

@@ -57,6 +57,7 @@ def _worker(rank, world, port, out):
         ref.grad.copy_(g)
         ref.update_apply()
     torch.cuda.synchronize()
+    assert not peer.peer_timed_out(), "the in-kernel exchange gave up waiting for a peer"
     th = peer.theta.cpu()
     gathered = [torch.empty_like(th) for _ in range(world)]
     dist.all_gather(gathered, th)
