@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libmarlb200.so")
+SO_PATH = os.environ.get("MARL_B200_SO") or os.path.join(_HERE, "csrc", "libmarlb200.so")   # MARL_B200_SO: a profiling build of the same library
 _lib = None
 
 

@@ -1,6 +1,7 @@
 // core.cu -- error reporting and device checks shared by every entry point of libmarlb200.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace marl {
 
@@ -32,7 +33,9 @@ int check_device(int device) {
   return MARL_OK;
 }
 
-static int g_tc_forward = 1, g_tc_backward = 1;
+static int env_flag(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? (v[0] != '0') : dflt; }
+static int g_tc_forward = 1, g_tc_backward = 1, g_tc_pingpong = env_flag("MARL_TC_PINGPONG", 1);   // the environment variable only moves the default
+int tc_pingpong_enabled() { return g_tc_pingpong; }
 int tc_forward_enabled() { return g_tc_forward; }
 int tc_backward_enabled() { return g_tc_backward; }
 
@@ -44,6 +47,9 @@ extern "C" {
 int marl_set_option(const char* name, int32_t value) {
   if (name && strcmp(name, "tensor_core_forward") == 0) { marl::g_tc_forward = value ? 1 : 0; return MARL_OK; }
   if (name && strcmp(name, "tensor_core_backward") == 0) { marl::g_tc_backward = value ? 1 : 0; return MARL_OK; }
+  /* 1 (default): tensor-core kernels with two accumulator buffers in TMEM -- the epilogue of one 128-row tile runs under the MMAs of the
+   * next; 0: the round-1 kernels (one tile at a time, tensor and CUDA-core phases alternate) */
+  if (name && strcmp(name, "tensor_core_pingpong") == 0) { marl::g_tc_pingpong = value ? 1 : 0; return MARL_OK; }
   marl::set_error("marl_set_option: unknown option '%s'", name ? name : "(null)");
   return MARL_EINVAL;
 }

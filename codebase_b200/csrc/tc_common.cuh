@@ -97,6 +97,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4, LBO 1, SBO 1024 B,
 // version 1, layout type 2
 __device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_addr) {
@@ -206,5 +209,90 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const float (&v)[8]) {
                "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
+
+// ---- the tensor-core training pass (tc_train.cu: one tile at a time; tc_train2.cu: two accumulators) -----------------------------------------------
+constexpr int kRowRec = 16;  // floats per row record: [0] g, [1] act, [2..3] spare, [4..7] mask1, [8..11] mask2
+
+struct TcTrainParams {
+  RowPlan plan; RowSource src; NetLayout lay;
+  const uint8_t* images;      // forward images [n_nets][kImageBytes]
+  const uint8_t* bwd_images;  // backward images [n_nets][kBwdImageBytes]
+  float* q_out;               // [rows][out] online outputs (optional)
+  // H1, H2, dH1: [32 float4 column chunks][rows][4] -- chunk-major, so that a warp whose lanes are 32 consecutive rows writes or
+  // reads 512 contiguous bytes per instruction (row-major rows of 512 B cost one cache line per lane and instruction)
+  float* h1g; float* h2g; float* dh1g; size_t rows;
+  float* rec;                 // [rows][kRowRec] row records
+  float* xg;                  // [rows][kMaxObsDim] gathered observation rows (zero padded to the staged width): the weight-gradient
+                              // kernel reads them without chasing the episode index again
+  const float* tq; const float* td_ext; float gamma; int double_q;
+  float* scratch; int scratch_pitch; float* loss_part;
+};
+
+int tc_train2_init();
+int launch_tc_dqn_fwd2(const TcTrainParams& p, int grid, cudaStream_t st);
+int launch_tc_dh12(const TcTrainParams& p, int grid, cudaStream_t st);
+
+// ---- pieces shared by the two-accumulator (ping-pong) kernels: tc_forward2_kernel, tc_dqn_fwd2_kernel, tc_dh12_kernel ---------------------------
+constexpr int kTailBytes = kImageBytes - kOffB1;                    // b1 | b2 | b3 | FP32 W3
+constexpr uint32_t kColD0 = 256, kColD1 = 384;                      // TMEM: A hi [0,128) | A lo [128,256) | D0 | D1
+// a 128 x 128 x 128 product in TS form (A hi | lo in the TMEM A columns, B = K-major SWIZZLE_128B hi / lo images of four 32-feature panels):
+// 3 terms x 16 k-steps, fully unrolled, issued by one thread
+__device__ __forceinline__ void issue_kmajor_ts(uint32_t tmem, uint32_t d_col, uint32_t b_hi, uint32_t b_lo) {
+  const uint32_t idesc = idesc_tf32(kHidden);
+  const uint64_t dhi = kmajor_desc(b_hi), dlo = kmajor_desc(b_lo);
+#pragma unroll
+  for (int term = 0; term < 3; ++term)
+#pragma unroll
+    for (int ks = 0; ks < kHidden / 8; ++ks)
+      mma_tf32_ts(tmem + d_col, tmem + (term == 0 ? kColALo : kColAHi) + ks * 8, (term == 1 ? dlo : dhi) + (uint32_t)(((ks >> 2) * kPanelBytes + (ks & 3) * 32) >> 4), idesc,
+                  (term | ks) ? 1u : 0u);
+}
+// layer 1 in SS form: D = X_lo*W_hi + X_hi*W_lo + X_hi*W_hi, both operands K-major SWIZZLE_128B panels of 32 features (one thread)
+__device__ __forceinline__ void issue_l1_ss(uint32_t d_tmem, uint32_t xs_hi, uint32_t xs_lo, uint32_t w_hi, uint32_t w_lo, int ksteps) {
+  const uint32_t idesc = idesc_tf32(kHidden);
+  const uint64_t ahi = kmajor_desc(xs_hi), alo = kmajor_desc(xs_lo), bhi = kmajor_desc(w_hi), blo = kmajor_desc(w_lo);
+#pragma unroll
+  for (int term = 0; term < 3; ++term)
+#pragma unroll
+    for (int ks = 0; ks < kMaxObsDim / 8; ++ks)
+      if (ks < ksteps) mma_tf32_ss(d_tmem, (term == 0 ? alo : ahi) + (uint32_t)((ks * 32) >> 4), (term == 1 ? blo : bhi) + (uint32_t)((ks * 32) >> 4), idesc, (term | ks) ? 1u : 0u);
+}
+// this thread's 8 observation columns of its row -> the K-major SWIZZLE_128B X tile (hi | lo): 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+__device__ __forceinline__ void stage_x_tile(uint8_t* xs, int r, int cq, const float (&x)[8]) {
+  float4 h0, h1, l0, l1;
+  tf32_split(x[0], h0.x, l0.x); tf32_split(x[1], h0.y, l0.y); tf32_split(x[2], h0.z, l0.z); tf32_split(x[3], h0.w, l0.w);
+  tf32_split(x[4], h1.x, l1.x); tf32_split(x[5], h1.y, l1.y); tf32_split(x[6], h1.z, l1.z); tf32_split(x[7], h1.w, l1.w);
+  const int o0 = r * 128 + (((2 * cq) ^ (r & 7)) << 4), o1 = r * 128 + (((2 * cq + 1) ^ (r & 7)) << 4);
+  *reinterpret_cast<float4*>(xs + o0) = h0; *reinterpret_cast<float4*>(xs + o1) = h1;
+  *reinterpret_cast<float4*>(xs + kPanelBytes + o0) = l0; *reinterpret_cast<float4*>(xs + kPanelBytes + o1) = l1;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// head on the CUDA cores: this thread's 32 columns of relu(D + b2) against the FP32 copy of W3 -> 8 partial outputs of its row.  Packed FP32
+// (fma.rn.f32x2, sm_100): even and odd columns accumulate in the two halves of a register pair and are added at the end (fixed order).
+__device__ __forceinline__ void head_partial(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const float* b2c, const float4* w3c, int out, float (&q)[kOutPad]) {
+  float2 q2[kOutPad];
+#pragma unroll
+  for (int a = 0; a < kOutPad; ++a) q2[a] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t (&acc)[16] = g < 4 ? ra : rb;
+    const int o = 4 * (g & 3);
+    const float4 bb = *reinterpret_cast<const float4*>(b2c + 4 * g);
+    float2 h01 = __fadd2_rn(make_float2(__uint_as_float(acc[o]), __uint_as_float(acc[o + 1])), make_float2(bb.x, bb.y));
+    float2 h23 = __fadd2_rn(make_float2(__uint_as_float(acc[o + 2]), __uint_as_float(acc[o + 3])), make_float2(bb.z, bb.w));
+    h01.x = fmaxf(h01.x, 0.f); h01.y = fmaxf(h01.y, 0.f); h23.x = fmaxf(h23.x, 0.f); h23.y = fmaxf(h23.y, 0.f);
+#pragma unroll
+    for (int a = 0; a < kOutPad; ++a) {
+      if (a < out) {
+        const float4 w = w3c[a * (kHidden / 4) + g];
+        q2[a] = __ffma2_rn(h23, make_float2(w.z, w.w), __ffma2_rn(h01, make_float2(w.x, w.y), q2[a]));
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < kOutPad; ++a) q[a] = q2[a].x + q2[a].y;
+}
+
 
 }  // namespace marl

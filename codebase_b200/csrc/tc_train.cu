@@ -14,23 +14,6 @@
 
 namespace marl {
 
-constexpr int kRowRec = 16;  // floats per row record: [0] g, [1] act, [2..3] spare, [4..7] mask1, [8..11] mask2
-
-struct TcTrainParams {
-  RowPlan plan; RowSource src; NetLayout lay;
-  const uint8_t* images;      // forward images [n_nets][kImageBytes]
-  const uint8_t* bwd_images;  // backward images [n_nets][kBwdImageBytes]
-  float* q_out;               // [rows][out] online outputs (optional)
-  // H1, H2, dH1: [32 float4 column chunks][rows][4] -- chunk-major, so that a warp whose lanes are 32 consecutive rows writes or
-  // reads 512 contiguous bytes per instruction (row-major rows of 512 B cost one cache line per lane and instruction)
-  float* h1g; float* h2g; float* dh1g; size_t rows;
-  float* rec;                 // [rows][kRowRec] row records
-  float* xg;                  // [rows][kMaxObsDim] gathered observation rows (zero padded to the staged width): the weight-gradient
-                              // kernel reads them without chasing the episode index again
-  const float* tq; const float* td_ext; float gamma; int double_q;
-  float* scratch; int scratch_pitch; float* loss_part;
-};
-
 __device__ __forceinline__ size_t dst_of(const RowPlan& plan, const RowSource& src, int net, int vr, int& agent, int& unit, int& off) {
   decode_row(plan, net, vr, agent, unit, off);
   return src.mode == 0 ? ((size_t)unit * src.N + agent) : (((size_t)agent * plan.units_per_agent + unit) * plan.unit_rows + off);
@@ -428,9 +411,6 @@ __device__ __forceinline__ void stage4(uint8_t* hi_img, uint8_t* lo_img, int r, 
   *reinterpret_cast<float4*>(hi_img + off) = h;
   *reinterpret_cast<float4*>(lo_img + off) = l;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -668,7 +648,7 @@ int tc_train_init() {
   MARL_CUDA_TRY(cudaFuncSetAttribute(tc_dqn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdTrainSmem));
   MARL_CUDA_TRY(cudaFuncSetAttribute(tc_dh1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDh1Smem));
   MARL_CUDA_TRY(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
-  return MARL_OK;
+  return tc_train2_init();
 }
 
 // all three kernels walk the same episode-aligned row split, so the per-CTA partials line up with ReduceParams::cta_begin
@@ -680,9 +660,12 @@ int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_
   p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
   p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
-  MARL_CUDA_TRY(launch_pdl(tc_dqn_fwd_kernel, dim3(grid), dim3(kTrThreads), kFwdTrainSmem, st, p));
+  const bool pingpong = tc_pingpong_enabled() && p.src.mode == 1;   // two-accumulator kernels (tc_train2.cu)
+  if (pingpong) { if (int rc = launch_tc_dqn_fwd2(p, grid, st)) return rc; }
+  else MARL_CUDA_TRY(launch_pdl(tc_dqn_fwd_kernel, dim3(grid), dim3(kTrThreads), kFwdTrainSmem, st, p));
   if (between) MARL_CUDA_TRY(cudaEventRecord(between[0], st));
-  MARL_CUDA_TRY(launch_pdl(tc_dh1_kernel, dim3(grid), dim3(kTrThreads), kDh1Smem, st, p));
+  if (pingpong) { if (int rc = launch_tc_dh12(p, grid, st)) return rc; }
+  else MARL_CUDA_TRY(launch_pdl(tc_dh1_kernel, dim3(grid), dim3(kTrThreads), kDh1Smem, st, p));
   if (between) MARL_CUDA_TRY(cudaEventRecord(between[1], st));
   MARL_CUDA_TRY(launch_pdl(tc_dw_kernel, dim3(grid), dim3(kDwThreads), kDwSmemBytes, st, p));
   return MARL_OK;

@@ -155,6 +155,20 @@ def dqn_loss(theta, theta_tgt, agent_net, in_dim, out_dim, batch, hp: DqnHP):
     return (loss * filled).sum() / filled.sum()
 
 
+def double_q_margin(st: DqnState, batch, hp: DqnHP):
+    """Smallest gap between the best and the second-best ONLINE Q-value over every (agent, filled step t, episode) whose row t + 1 feeds the
+    double-Q argmax (VDN: the same, per agent).  The argmax is discontinuous: when this margin is below the forward passes' ~1e-6 agreement, two
+    correct implementations may pick different target actions and their gradients then differ by ~1 / filled-steps -- not a defect."""
+    if not hp.double_q:
+        return float("inf")
+    with torch.no_grad():
+        q = torch.stack(agents_forward(st.theta, st.agent_net, list(batch["obss"]), st.in_dim, st.out_dim))[:, 1:]     # (N, T, B, A)
+        top2 = q.topk(2, dim=-1).values
+        gap = (top2[..., 0] - top2[..., 1]) / top2[..., 0].abs().clamp_min(1.0)
+        mask = batch["filled"].unsqueeze(0).expand_as(gap) > 0
+        return float(gap[mask].min()) if bool(mask.any()) else float("inf")
+
+
 def dqn_update(st: DqnState, batch, hp: DqnHP):
     """QNetwork.update: returns dict(loss, grad (before clipping), grad_norm)."""
     theta = st.theta.clone().requires_grad_(True)

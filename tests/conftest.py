@@ -18,3 +18,23 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "refsrc" in item.keywords and not have_ref:
             item.add_marker(pytest.mark.skip(reason="/root/reference is not present on this box"))
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything(request):
+    """Every test starts from the same random state: model initialisation (torch's orthogonal init) must not vary from run to run.  The DQN
+    family's double-Q argmax is discontinuous -- a GPU / oracle difference of 1e-7 in two nearly tied online Q-values selects a different target
+    action and moves the gradient by ~1/filled-steps -- so an unseeded initialisation made ~8 % of the random cases fail at random
+    (tools/grad_stress.py).  Tests that compare against the oracle additionally check the oracle's argmax margin (oracle.learner_ref.double_q_margin)."""
+    import random
+
+    import numpy as np
+
+    random.seed(12345); np.random.seed(12345)
+    try:
+        import torch
+
+        torch.manual_seed(12345)
+    except ImportError:
+        pass
+    yield

@@ -20,7 +20,8 @@ def _close(a, b, rtol=1e-5, atol=1e-5):
 
 
 def _close_scaled(a, b, tol=1e-5):
-    """element-wise, relative to the tensor's own scale (Adam's second moment lives at 1e-6 .. 1e-10)"""
+    """element-wise, relative to the tensor's own scale (Adam's second moment lives at 1e-6 .. 1e-10).  For v = (1 - beta2) g^2 pass tol=2e-5:
+    a relative gradient error e shows up as 2e in v, so 2e-5 on v is the 1e-5 bar on g."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     scale = max(float(np.abs(b).max()), 1e-30)
     assert np.abs(a - b).max() <= tol * scale, (float(np.abs(a - b).max()), scale)
@@ -81,7 +82,7 @@ def test_update_matches_reference_golden(name):
             _close(ret.permute(2, 1, 0).cpu().numpy(), g["returns0"])
     am, av = m.adam_m.cpu().numpy(), m.adam_v.cpu().numpy()   # element-wise against the reference optimiser's state
     _close_scaled(am[: m.n_actor], g["actor_adam_m_final"]); _close_scaled(am[m.n_actor:], g["critic_adam_m_final"])
-    _close_scaled(av[: m.n_actor], g["actor_adam_v_final"]); _close_scaled(av[m.n_actor:], g["critic_adam_v_final"])
+    _close_scaled(av[: m.n_actor], g["actor_adam_v_final"], tol=2e-5); _close_scaled(av[m.n_actor:], g["critic_adam_v_final"], tol=2e-5)
     th, tg = m.theta.cpu().numpy(), m.theta_tgt.cpu().numpy()
     for got, want in ((th[: m.n_actor], g["actor_final"]), (th[m.n_actor:], g["critic_final"]), (tg, g["target_final"])):
         d = np.abs(got - want)
@@ -117,7 +118,7 @@ def test_update_matches_oracle_on_random_batches(sharing, P, n_agents, clip):
         _close_scaled(_clipped(gr[:n] / gr[n + 1], clip), np.concatenate([want["grad_clipped"]["actor"].numpy(), want["grad_clipped"]["critic"].numpy()]))
         met = m.metrics_dict(m.update_apply(step))
         _close_scaled(m.adam_m.cpu().numpy(), np.concatenate([st.m["actor"].numpy(), st.m["critic"].numpy()]))
-        _close_scaled(m.adam_v.cpu().numpy(), np.concatenate([st.v["actor"].numpy(), st.v["critic"].numpy()]))
+        _close_scaled(m.adam_v.cpu().numpy(), np.concatenate([st.v["actor"].numpy(), st.v["critic"].numpy()]), tol=2e-5)
         _close([met["loss"], met["actor_loss"], met["value_loss"], met["entropy"]], [want["loss"], want["actor_loss"], want["value_loss"], want["entropy"]])
         vt, ret, adv = m.scratch(P, T)
         _close(ret.permute(2, 1, 0).cpu().numpy(), want["returns"].numpy())

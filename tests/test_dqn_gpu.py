@@ -22,7 +22,8 @@ def _close(a, b, rtol=1e-5, atol=1e-5):
 
 
 def _close_scaled(a, b, tol=1e-5):
-    """element-wise, relative to the tensor's own scale (Adam's second moment lives at 1e-6 .. 1e-10)"""
+    """element-wise, relative to the tensor's own scale (Adam's second moment lives at 1e-6 .. 1e-10).  For v = (1 - beta2) g^2 pass tol=2e-5:
+    a relative gradient error e shows up as 2e in v, so 2e-5 on v is the 1e-5 bar on g."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     scale = max(float(np.abs(b).max()), 1e-30)
     assert np.abs(a - b).max() <= tol * scale, (float(np.abs(a - b).max()), scale)
@@ -97,15 +98,28 @@ def test_update_matches_reference_golden(name):
         _close(met[0].item(), g["losses"][u])
     # Adam state element-wise against the reference optimiser's exp_avg / exp_avg_sq: the quantile bound on theta cannot hide a defect here
     _close_scaled(m.adam_m.cpu().numpy(), g["adam_m_final"])
-    _close_scaled(m.adam_v.cpu().numpy(), g["adam_v_final"])
+    _close_scaled(m.adam_v.cpu().numpy(), g["adam_v_final"], tol=2e-5)
     d = np.abs(m.theta.cpu().numpy() - g["theta_final"])
     assert np.quantile(d, 0.999) < 1e-5 and d.max() < 2 * hp.lr * len(g["losses"]) + 1e-6, (np.quantile(d, 0.999), d.max())
     dt = np.abs(m.theta_tgt.cpu().numpy() - g["target_final"])
     assert np.quantile(dt, 0.999) < 1e-5
 
 
+TIE = 2e-5   # relative gap of the two best online Q-values under which the double-Q argmax may legitimately differ between two implementations
+
+
 @pytest.mark.parametrize("mixer,sharing,B,n_agents", [(0, False, 64, 2), (0, False, 1024, 2), (1, False, 257, 2), (0, True, 100, 2), (0, [0, 1, 0], 33, 3), (1, False, 48, 4)])
 def test_update_matches_oracle_on_random_batches(mixer, sharing, B, n_agents):
+    """Three glued updates against the oracle.  A case whose oracle argmax margin is below TIE is re-drawn (new initialisation), at most four times:
+    with a healthy margin every mismatch is a defect."""
+    for attempt in range(5):
+        torch.manual_seed(1000 * attempt + B)
+        if _three_glued_updates(mixer, sharing, B, n_agents) == "ok":
+            return
+    pytest.fail("five initialisations in a row hit a double-Q near-tie: not plausible")
+
+
+def _three_glued_updates(mixer, sharing, B, n_agents):
     rng = np.random.default_rng(B)
     hp = lr.DqnHP(mixer=mixer, target_update_interval_or_tau=2)
     m = _model("VDNetwork" if mixer else "QNetwork", sharing, hp, n_agents=n_agents, max_batch=B)
@@ -124,7 +138,10 @@ def test_update_matches_oracle_on_random_batches(mixer, sharing, B, n_agents):
             done[e, length[e]] = rng.random() < 0.7
         store = dict(obs=obs, act=act, rew=rew, done=done, filled=filled)
         idx = rng.integers(0, cap, size=B).astype(np.int32)
-        want = lr.dqn_update(st, lr.batch_from_store(store, idx), hp)
+        batch = lr.batch_from_store(store, idx)
+        if lr.double_q_margin(st, batch, hp) < TIE:
+            return "near-tie"   # the comparison would be a coin toss on which target action is selected
+        want = lr.dqn_update(st, batch, hp)
         ts = _store_to_device(store, m.device)
         m.update_grads(ts, torch.tensor(idx, device="cuda"))
         gr = m.grad.cpu().numpy()
@@ -133,13 +150,14 @@ def test_update_matches_oracle_on_random_batches(mixer, sharing, B, n_agents):
         _close_scaled(_clipped(gr[:m.n_params] / gr[m.n_params + 1], hp.grad_clip), want["grad_clipped"].numpy())
         met = m.update_apply().cpu().numpy()
         _close(met[0], want["loss"]); _close(met[1], want["grad_norm"], rtol=1e-4)
-        _close_scaled(m.adam_m.cpu().numpy(), st.m.numpy()); _close_scaled(m.adam_v.cpu().numpy(), st.v.numpy())
+        _close_scaled(m.adam_m.cpu().numpy(), st.m.numpy()); _close_scaled(m.adam_v.cpu().numpy(), st.v.numpy(), tol=2e-5)
         d = np.abs(m.theta.cpu().numpy() - st.theta.numpy())
         assert np.quantile(d, 0.999) < 1e-5 and d.max() < 2 * hp.lr * (u + 1) + 1e-6
         # keep the two trajectories glued so that later steps compare like for like
         m.theta.copy_(st.theta); m.theta_tgt.copy_(st.theta_tgt); m.adam_m.copy_(st.m); m.adam_v.copy_(st.v)
         m.params_changed()  # direct writes: cached derived data (packed target image) must be rebuilt
     assert m.updates == 3
+    return "ok"
 
 
 def test_reference_style_update_call_and_state_dict_roundtrip():

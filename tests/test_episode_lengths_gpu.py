@@ -8,6 +8,8 @@ import torch
 
 from oracle import learner_ref as lr
 
+from tests.helpers import check_margin, redraw_on_near_tie
+
 pytestmark = pytest.mark.gpu
 D, A, N = 15, 6, 2
 
@@ -45,6 +47,7 @@ def _to_dev(s, T, device):
 
 
 @pytest.mark.parametrize("T,B,mixer", [(50, 128, 0), (50, 700, 1), (7, 1024, 0), (100, 33, 0), (1, 512, 0), (127, 16, 1), (128, 9, 0)])
+@redraw_on_near_tie
 def test_dqn_update_various_T(T, B, mixer):
     from codebase_b200.dqn import model as M
 
@@ -56,7 +59,9 @@ def test_dqn_update_various_T(T, B, mixer):
     cap = 300
     s = _store(rng, cap, T, bool(mixer))
     idx = rng.integers(0, cap, size=B).astype(np.int32)
-    want = lr.dqn_update(st, lr.batch_from_store(s, idx), hp)
+    batch = lr.batch_from_store(s, idx)
+    check_margin(lr, st, batch, hp)   # near-tie in the double-Q argmax: re-drawn by the decorator
+    want = lr.dqn_update(st, batch, hp)
     m.update_grads(_to_dev(s, T, m.device), torch.tensor(idx, device="cuda"))
     gr = m.grad.cpu().numpy()
     n = m.n_params

@@ -8,6 +8,8 @@ import torch
 
 from oracle import learner_ref as lr
 
+from tests.helpers import check_margin, redraw_on_near_tie
+
 pytestmark = pytest.mark.gpu
 T, A = 25, 6
 
@@ -46,6 +48,7 @@ def _to_store(s, device):
 
 
 @pytest.mark.parametrize("mixer,n_agents,D,B", [(0, 4, 27, 96), (1, 4, 27, 300), (0, 2, 17, 64), (0, 3, 32, 40)])
+@redraw_on_near_tie
 def test_dqn_family_update_wide_obs(mixer, n_agents, D, B):
     from codebase_b200.dqn import model as M
 
@@ -61,7 +64,9 @@ def test_dqn_family_update_wide_obs(mixer, n_agents, D, B):
     _close(m.q_values(torch.tensor(obs, device="cuda")).cpu().numpy(), want_q)
     store = _random_store(rng, 200, n_agents, D, bool(mixer))
     idx = rng.integers(0, 200, size=B).astype(np.int32)
-    want = lr.dqn_update(st, lr.batch_from_store(store, idx), hp)
+    batch = lr.batch_from_store(store, idx)
+    check_margin(lr, st, batch, hp)   # near-tie in the double-Q argmax: re-drawn by the decorator
+    want = lr.dqn_update(st, batch, hp)
     m.update_grads(_to_store(store, m.device), torch.tensor(idx, device="cuda"))
     gr = m.grad.cpu().numpy()
     scale = max(1.0, float(np.abs(want["grad"].numpy()).max()))
