@@ -94,6 +94,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 int check_device(int device);
 int tc_forward_enabled();
 int tc_backward_enabled();
-int tc_pingpong_enabled();
+int tc_pingpong_enabled(int which);   // 0: forward kernels, 1: dH1 kernel
 
 }  // namespace marl

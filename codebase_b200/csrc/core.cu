@@ -1,5 +1,5 @@
 // core.cu -- error reporting and device checks shared by every entry point of libmarlb200.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <string.h>
 #include <stdlib.h>
 
@@ -33,9 +33,11 @@ int check_device(int device) {
   return MARL_OK;
 }
 
-static int env_flag(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? (v[0] != '0') : dflt; }
-static int g_tc_forward = 1, g_tc_backward = 1, g_tc_pingpong = env_flag("MARL_TC_PINGPONG", 1);   // the environment variable only moves the default
-int tc_pingpong_enabled() { return g_tc_pingpong; }
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+// bit 0: forward kernels (tc_forward2_kernel, tc_dqn_fwd2_kernel), bit 1: dH1 kernel (tc_dh12_kernel).  Default 2: with ~3 tiles per CTA the
+// two-accumulator forward kernels do not amortise their pipeline fill (measured slower than the one-tile kernels), the dH1 kernel does.
+static int g_tc_forward = 1, g_tc_backward = 1, g_tc_pingpong = env_int("MARL_TC_PINGPONG", 2);   // the environment variable only moves the default
+int tc_pingpong_enabled(int which) { return (g_tc_pingpong >> which) & 1; }
 int tc_forward_enabled() { return g_tc_forward; }
 int tc_backward_enabled() { return g_tc_backward; }
 
@@ -47,11 +49,25 @@ extern "C" {
 int marl_set_option(const char* name, int32_t value) {
   if (name && strcmp(name, "tensor_core_forward") == 0) { marl::g_tc_forward = value ? 1 : 0; return MARL_OK; }
   if (name && strcmp(name, "tensor_core_backward") == 0) { marl::g_tc_backward = value ? 1 : 0; return MARL_OK; }
-  /* 1 (default): tensor-core kernels with two accumulator buffers in TMEM -- the epilogue of one 128-row tile runs under the MMAs of the
-   * next; 0: the round-1 kernels (one tile at a time, tensor and CUDA-core phases alternate) */
-  if (name && strcmp(name, "tensor_core_pingpong") == 0) { marl::g_tc_pingpong = value ? 1 : 0; return MARL_OK; }
+  /* bit mask of the tensor-core kernels that use two accumulator buffers in TMEM (the epilogue of one 128-row tile runs under the MMAs of the
+   * next): bit 0 = forward kernels, bit 1 = dH1 kernel; default 2.  0: one tile at a time everywhere */
+  if (name && strcmp(name, "tensor_core_pingpong") == 0) { marl::g_tc_pingpong = value & 3; return MARL_OK; }
   marl::set_error("marl_set_option: unknown option '%s'", name ? name : "(null)");
   return MARL_EINVAL;
+}
+/* Profiling builds only (MARL_NVCC_DEFINES=-DMARL_TC_TIMESTAMPS, tools/ts_timeline.py): the timeline probes of kernel `which` (0 forward, 1 training
+ * forward, 2 dH1, 3 weight gradients, 4 reduce + Adam, 5 dH1 with two accumulators) as [160 CTAs][32 slots][globaltimer ns, clock64] -> host memory;
+ * product builds return MARL_EINVAL. */
+int marl_debug_timestamps(int32_t which, uint64_t* out) {
+  int rc = -1;
+  unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
+  switch (which) {
+    case 0: rc = marl::tsg_forward(o); break; case 1: rc = marl::tsg_fwd(o); break; case 2: rc = marl::tsg_dh1(o); break;
+    case 3: rc = marl::tsg_dw(o); break; case 4: rc = marl::tsg_adam(o); break; case 5: rc = marl::tsg_dh12(o); break;
+    default: break;
+  }
+  if (rc != 0) { marl::set_error("marl_debug_timestamps: kernel %d has no probes in this build (build with -DMARL_TC_TIMESTAMPS)", (int)which); return MARL_EINVAL; }
+  return MARL_OK;
 }
 int marl_version(void) { return MARL_ABI_VERSION; }
 const char* marl_last_error(void) { return marl::g_err; }

@@ -517,6 +517,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* barrier, unsign
   __syncthreads();
 }
 
+TSG_DEFINE(g_ts_adam)
+TSG_GETTER(tsg_adam, g_ts_adam)
 template <bool XCHG>
 __global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams rp, AdamParams ap, XchgParams xp, SampleParams sp, int pb, int ns,
                                                                     unsigned long long* barrier, unsigned long long target) {
@@ -526,8 +528,10 @@ __global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams
   // pb parameters (a multiple of 32) x ns CTA-slices per block, blockDim.x = pb * ns
   const int t = threadIdx.x, q = t / pb, lane = t - q * pb;
   const int i = blockIdx.x * pb + lane, n = rp.n_nets * rp.P;
+  TSG(g_ts_adam, 0);
   pdl_wait();
   pdl_launch_dependents();
+  TSG(g_ts_adam, 1);
   float s = 0.f;
   if (i < n) {
     const int net = i / rp.P, j = i - net * rp.P;
@@ -548,6 +552,7 @@ __global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams
   if (q == 0 && i < ap.n) { m_i = ap.m[i]; v_i = ap.v[i]; th_i = ap.theta[i]; }
   part[q][lane] = s;
   __syncthreads();
+  TSG(g_ts_adam, 2);
   float g = 0.f;
   // this rank's copy inside rank r's buffer: base_r + ((epoch & 1) * world + rank) * slot_floats
   const size_t push_off = XCHG ? ((size_t)(xp.epoch & 1ULL) * xp.world + xp.rank) * xp.slot_floats : 0;
@@ -607,7 +612,9 @@ __global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams
     for (int k = 1; k < pb / 32; ++k) x += red[k];
     rp.sumsq_part[blockIdx.x] = x;
   }
+  TSG(g_ts_adam, 3);
   grid_barrier(barrier, target, false);   // every block's sum of squares (and block 0's statistics) are visible after it
+  TSG(g_ts_adam, 4);
   // ---- every block: global norm from the per-block sums (fixed order: lane k adds blocks k, k + 32, ..., then a shuffle tree) ----
   if (t < 32) {
     float x = 0.f;
@@ -650,6 +657,7 @@ __global__ void __launch_bounds__(kFusedThreads) reduce_adam_kernel(ReduceParams
       sp.idx[k] = (int32_t)bounded(pick(b, k & 3), (uint32_t)sp.n_valid);
     }
   }
+  TSG(g_ts_adam, 31);
   if (blockIdx.x == 0 && t == 0 && ap.loss_out) {
     ap.loss_out[0] = st4[0] * inv_fill; ap.loss_out[1] = norm; ap.loss_out[2] = st4[2] * inv_fill;
     ap.loss_out[3] = st4[3] * inv_fill; ap.loss_out[4] = fill;

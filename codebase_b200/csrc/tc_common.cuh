@@ -78,6 +78,22 @@ constexpr int kTsBytes = 0;
 #define TS_DUMP(name)
 #endif
 
+// Global timeline probes of the same builds: thread 0 of every CTA stores %globaltimer (ns) and clock64() per probe slot into a per-kernel
+// device buffer; tools/ts_timeline.py reads them back through marl_debug_timestamps (launch gaps, prologues, per-tile phases, tail skew).
+#ifdef MARL_TC_TIMESTAMPS
+constexpr int kTsgCtas = 160, kTsgSlots = 32;
+#define TSG_DEFINE(name) static __device__ unsigned long long name[kTsgCtas][kTsgSlots][2];
+#define TSG(name, slot) do { if (threadIdx.x == 0 && blockIdx.x < kTsgCtas && (slot) < kTsgSlots) { unsigned long long g_; \
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); name[blockIdx.x][(slot)][0] = g_; name[blockIdx.x][(slot)][1] = (unsigned long long)clock64(); } } while (0)
+#define TSG_GETTER(fn, name) int fn(unsigned long long* out) { return cudaMemcpyFromSymbol(out, name, sizeof(name)) == cudaSuccess ? 0 : -1; }
+#else
+#define TSG_DEFINE(name)
+#define TSG(name, slot)
+#define TSG_GETTER(fn, name) int fn(unsigned long long*) { return -1; }
+#endif
+int tsg_forward(unsigned long long* out); int tsg_fwd(unsigned long long* out); int tsg_dh1(unsigned long long* out); int tsg_dw(unsigned long long* out);
+int tsg_dh12(unsigned long long* out); int tsg_adam(unsigned long long* out);
+
 // dynamic shared memory rounded up to 1024 bytes (swizzle atoms), keeping the pointer in the shared address space so that the
 // compiler emits LDS / STS rather than generic loads and stores
 __device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) { return raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(raw) & 1023u)) & 1023u); }
@@ -159,6 +175,14 @@ __device__ __forceinline__ void tma_forward_image(uint32_t smem_base, const uint
   tma_image_range(smem_base, src, kOffW2Hi, kOffW3Hi, bars + 1);
   mbar_expect_tx(bars + 2, (uint32_t)(kOffB1 - kOffW3Hi));
   tma_image_range(smem_base, src, kOffW3Hi, kOffB1, bars + 2);
+}
+// the same without the tensor-core operand copies of W3 (head on the CUDA cores): bars[0] <- W1 + biases + FP32 W3, bars[1] <- W2
+__device__ __forceinline__ void tma_forward_image_nohead(uint32_t smem_base, const uint8_t* src, uint64_t* bars) {
+  mbar_expect_tx(bars + 0, (uint32_t)(kOffW2Hi + (kImageBytes - kOffB1)));
+  tma_image_range(smem_base, src, kOffW1Hi, kOffW2Hi, bars + 0);
+  tma_image_range(smem_base, src, kOffB1, kImageBytes, bars + 0);
+  mbar_expect_tx(bars + 1, (uint32_t)(kOffW3Hi - kOffW2Hi));
+  tma_image_range(smem_base, src, kOffW2Hi, kOffW3Hi, bars + 1);
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -65,6 +65,8 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t d_col, uint3
   }
 }
 
+TSG_DEFINE(g_ts_forward)
+TSG_GETTER(tsg_forward, g_ts_forward)
 // 16 warps: warp w owns TMEM lane quarter (w & 3) -- rows 32 (w & 3) .. +31 of the tile -- and column quarter (w >> 2) of the
 // 128 hidden features, so that four warps per SM sub-partition overlap their TMEM / shared / global latencies.
 __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, const uint8_t* __restrict__ images) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   if (row_begin >= row_end) { pdl_wait(); return; }
-
+  TSG(g_ts_forward, 0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -84,9 +86,12 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); mbar_init(bar + 4, 1); fence_mbar_init(); }
   pdl_wait();   // nothing above touches global memory (PDL contract, common.cuh)
   pdl_launch_dependents();
+  TSG(g_ts_forward, 1);
   // the weight image is already in shared-memory layout: three TMA bulk copies (cp.async.bulk -> mbarrier, issued by one thread) in the
   // order the first tile needs them (W1 + biases, W2, W3), so that its first layer does not wait for the whole image
-  if (t == 0) tma_forward_image(smem_u32(smem), images + (size_t)net * kImageBytes, bar + 2);
+  // (the tensor-core operand copies of W3 are not loaded: the 6-wide head runs on the CUDA cores against the FP32 copy, and their 16 KB hold
+  // the head partials of column quarters 1..3)
+  if (t == 0) tma_forward_image_nohead(smem_u32(smem), images + (size_t)net * kImageBytes, bar + 2);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -96,10 +101,12 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   const float* b1 = reinterpret_cast<const float*>(smem + kOffB1);
   const float* b2 = reinterpret_cast<const float*>(smem + kOffB2);
   const float* b3 = reinterpret_cast<const float*>(smem + kOffB3);
+  const float4* w3f = reinterpret_cast<const float4*>(smem + kOffW3F);
+  float* part = reinterpret_cast<float*>(smem + kOffW3Hi);   // [3][128 rows][8]
   const int D = p.src.D, out = p.lay.out;
   const int k1steps = (D + 7) >> 3;
   const bool x_active = cq < k1steps;   // column quarter cq stages observation columns [8 cq, 8 cq + 8)
-  int image_groups_pending = 3;         // block-uniform
+  int image_groups_pending = 2;         // block-uniform: W1 + biases + FP32 W3, then W2
   uint32_t parity = 0;
   // this thread's 8 observation columns of its row (prefetched one tile ahead) and where the row's outputs go
   // (two steps, a barrier apart, so that neither waits on a load it has just issued: A = decode + episode index, B = the columns)
@@ -128,6 +135,8 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   RowKey key_nxt;
   fetch_a(row_begin, min(kTileRows, row_end - row_begin), key_nxt, dst_row);
   fetch_b(key_nxt, xin);
+  TSG(g_ts_forward, 2);
+  int ts_tile = 0; (void)ts_tile;
 
   for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
     const int nrows = min(kTileRows, row_end - vr0);
@@ -142,23 +151,22 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
       tmem_st8(lane_base + kColALo + 8 * cq, lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (image_groups_pending == 3) { mbar_wait(bar + 2, 0); image_groups_pending = 2; }   // W1 + biases have landed
+    if (image_groups_pending == 2) { mbar_wait(bar + 2, 0); image_groups_pending = 1; }   // W1 + biases + FP32 W3 have landed
     tc_fence_before();
     __syncthreads();
+    TSG(g_ts_forward, 3 + 6 * ts_tile);
     // ---- layer 1 -------------------------------------------------------------------------------------------------
     if (t == 0) {
       tc_fence_after();
       issue_layer<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
       mma_commit(bar);
     }
-    // prefetch the next tile's rows: the loads stay in flight under this tile's epilogues and MMAs
-    if (has_next) fetch_b(key_nxt, xnext);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
-    // ---- bias + ReLU, next A operand (twice: after layer 1 and after layer 2): this thread's 32 columns --------------------
-#pragma unroll 1
-    for (int layer = 0; layer < 2; ++layer) {
-      const float* bias = (layer == 0 ? b1 : b2) + c0;
+    TSG(g_ts_forward, 4 + 6 * ts_tile);
+    // ---- layer-1 epilogue: bias + ReLU, 3xTF32 split -> the A operand of layer 2 (this thread's 32 columns) ---------------------
+    {
+      const float* bias = b1 + c0;
       uint32_t ra[16], rb[16];
       tmem_ld16_issue(lane_base + kColD + c0, ra);
       tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
@@ -177,31 +185,48 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
         tmem_st16(lane_base + kColALo + c0 + 16 * half, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      if (image_groups_pending == 2 - layer) {   // W2 before the layer-2 MMAs, W3 before the head's
-        mbar_wait(bar + 3 + layer, 0);
-        image_groups_pending = 1 - layer;
-      }
+      if (image_groups_pending == 1) { mbar_wait(bar + 3, 0); image_groups_pending = 0; }   // W2
       tc_fence_before();
       __syncthreads();
+      TSG(g_ts_forward, 5 + 6 * ts_tile);
       if (t == 0) {
         tc_fence_after();
-        if (layer == 0) issue_layer<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
-        else issue_layer<kHidden / 8, kHeadRows, kHeadPanelBytes>(tmem, kColDHead, smem_base + kOffW3Hi, smem_base + kOffW3Lo, kHidden / 8);
+        issue_layer<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
         mma_commit(bar);
       }
+      // prefetch the next tile's rows under the layer-2 MMAs (the longest stretch in which the CUDA cores idle); the episode index they hang
+      // off was requested at the top of this tile
+      if (has_next) fetch_b(key_nxt, xnext);
       mbar_wait(bar, parity); parity ^= 1;
       tc_fence_after();
+      TSG(g_ts_forward, 6 + 6 * ts_tile);
     }
-    // ---- head epilogue: outputs to global (column quarter 0) ---------------------------------------------------------------
-    if (cq == 0) {
-      float v[16];
-      tmem_ld16(lane_base + kColDHead, v);
-      if (r < nrows) {
+    // ---- layer-2 epilogue + head on the CUDA cores: relu(D + b2) of this thread's 32 columns against the FP32 copy of W3; the partial sums of
+    // column quarters 1..3 travel through shared memory and column quarter 0 adds them in a fixed order ------------------------------------
+    {
+      uint32_t ra[16], rb[16];
+      tmem_ld16_issue(lane_base + kColD + c0, ra);
+      tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
+      tmem_ld_wait(ra);
+      tmem_ld_wait(rb);
+      float q[kOutPad];
+      head_partial(ra, rb, b2 + c0, w3f + (c0 >> 2), out, q);
+      if (cq > 0) {
+        float4* pp = reinterpret_cast<float4*>(part + ((size_t)(cq - 1) * kTileRows + r) * kOutPad);
+        pp[0] = make_float4(q[0], q[1], q[2], q[3]); pp[1] = make_float4(q[4], q[5], q[6], q[7]);
+      }
+      named_bar_sync(1 + lq, 128);   // the four warps of this lane quarter
+      TSG(g_ts_forward, 7 + 6 * ts_tile);
+      if (cq == 0 && r < nrows) {
         float* dst = p.out + dst_row * out;
 #pragma unroll
-        for (int o = 0; o < kOutPad; ++o) if (o < out) dst[o] = v[o] + b3[o];
+        for (int o = 0; o < kOutPad; ++o)
+          if (o < out) dst[o] = (((q[o] + part[((size_t)0 * kTileRows + r) * kOutPad + o]) + part[((size_t)1 * kTileRows + r) * kOutPad + o]) + part[((size_t)2 * kTileRows + r) * kOutPad + o]) + b3[o];
       }
+      // the next tile's partials are written two __syncthreads later: no second barrier needed
     }
+    TSG(g_ts_forward, 8 + 6 * ts_tile);
+    ts_tile += 1;
     dst_row = dst_next;
 #pragma unroll
     for (int j = 0; j < 8; ++j) xin[j] = xnext[j];
@@ -210,7 +235,9 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   }
   tc_fence_before();
   __syncthreads();
+  TSG(g_ts_forward, 30);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  TSG(g_ts_forward, 31);
 }
 
 // =====================================================================================================================
@@ -529,7 +556,7 @@ int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, ui
 }
 
 int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st) {
-  if (tc_pingpong_enabled()) MARL_CUDA_TRY(launch_pdl(tc_forward2_kernel, dim3(p.plan.cta_begin[p.plan.n_nets]), dim3(kP2Threads), kP2Smem, st, p, images));
+  if (tc_pingpong_enabled(0)) MARL_CUDA_TRY(launch_pdl(tc_forward2_kernel, dim3(p.plan.cta_begin[p.plan.n_nets]), dim3(kP2Threads), kP2Smem, st, p, images));
   else MARL_CUDA_TRY(launch_pdl(tc_forward_kernel, dim3(p.plan.cta_begin[p.plan.n_nets]), dim3(kTrThreads), kTcSmemBytes, st, p, images));
   return MARL_OK;
 }

@@ -45,6 +45,12 @@ __device__ __forceinline__ void split16(const float (&h)[16], float (&hi)[16], f
 // =====================================================================================================================
 // 1. online forward + TD head
 // =====================================================================================================================
+TSG_DEFINE(g_ts_fwd)
+TSG_GETTER(tsg_fwd, g_ts_fwd)
+TSG_DEFINE(g_ts_dh1)
+TSG_GETTER(tsg_dh1, g_ts_dh1)
+TSG_DEFINE(g_ts_dw)
+TSG_GETTER(tsg_dw, g_ts_dw)
 __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -61,6 +67,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     if (t < 4) p.loss_part[4 * blockIdx.x + t] = 0.f;
     return;
   }
+  TSG(g_ts_fwd, 0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -68,12 +75,16 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
   if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); mbar_init(bar + 4, 1); fence_mbar_init(); }
   pdl_wait();   // nothing above touches global memory
   pdl_launch_dependents();
+  TSG(g_ts_fwd, 1);
   // the weight image is already in shared-memory layout: three TMA bulk copies (cp.async.bulk -> mbarrier, issued by one thread) in the
   // order the first tile needs them (W1 + biases, W2, W3), so that its first layer does not wait for the whole image
-  if (t == 0) tma_forward_image(smem_u32(smem), p.images + (size_t)net * kImageBytes, bar + 2);
+  // (without the tensor-core operand copies of W3: the head runs on the CUDA cores against the FP32 copy; their 16 KB hold the head partials)
+  if (t == 0) tma_forward_image_nohead(smem_u32(smem), p.images + (size_t)net * kImageBytes, bar + 2);
   const float* b1 = reinterpret_cast<const float*>(smem + kOffB1);
   const float* b2 = reinterpret_cast<const float*>(smem + kOffB2);
   const float* b3 = reinterpret_cast<const float*>(smem + kOffB3);
+  const float4* w3f = reinterpret_cast<const float4*>(smem + kOffW3F);
+  float* part = reinterpret_cast<float*>(smem + kOffW3Hi);   // [3][128 rows][8]: head partials of column quarters 1..3
   const int D = p.src.D, A = p.lay.out, T = p.src.traj.T, B = p.plan.units_per_agent;
   const int k1steps = (D + 7) >> 3;
   const bool x_active = cq < k1steps;   // column quarter cq stages observation columns [8 cq, 8 cq + 8)
@@ -122,7 +133,9 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot, smem_base = smem_u32(smem), lane_base = tmem + ((uint32_t)(32 * lq) << 16);
-  int image_groups_pending = 3;   // block-uniform: groups not yet waited for
+  TSG(g_ts_fwd, 2);
+  int ts_tile = 0; (void)ts_tile;
+  int image_groups_pending = 2;   // block-uniform: groups not yet waited for (W1 + biases + FP32 W3, then W2)
   uint32_t parity = 0;
   float carry_q[kOutPad];         // thread 0: outputs of row 0 of the tile just finished, published after the next barrier
 #pragma unroll
@@ -145,9 +158,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (image_groups_pending == 3) { mbar_wait(bar + 2, 0); image_groups_pending = 2; }   // W1 + biases have landed
+    if (image_groups_pending == 2) { mbar_wait(bar + 2, 0); image_groups_pending = 1; }   // W1 + biases + FP32 W3 have landed
     tc_fence_before();
     __syncthreads();
+    TSG(g_ts_fwd, 3 + 6 * ts_tile);
     if (t == 0) {
       tc_fence_after();
       issue_kmajor<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
@@ -160,14 +174,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
     const size_t dst_row = cur.dst;
     const int agent = cur.agent, b = cur.b, tt = cur.tt, act = cur.act;
     const float rew = cur.rew; const uint8_t filled_u8 = cur.filled, done1_u8 = cur.done1;
-    // the next (lower) tile's rows: the loads stay in flight under this tile's MMAs and epilogues
-    if (has_next) fetch_b(key_nxt, nxt);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
-#pragma unroll 1
-    for (int layer = 0; layer < 2; ++layer) {
-      const float* bias = (layer == 0 ? b1 : b2) + c0;
-      float4* hg = reinterpret_cast<float4*>(layer == 0 ? p.h1g : p.h2g) + dst_row;
+    TSG(g_ts_fwd, 4 + 6 * ts_tile);
+    // ---- layer-1 epilogue: bias + ReLU -> H1 (FP32, chunk-major) + its mask -> global; 3xTF32 split -> the A operand of layer 2 ---------------
+    {
+      const float* bias = b1 + c0;
+      float4* hg = reinterpret_cast<float4*>(p.h1g) + dst_row;
       uint32_t ra[16], rb[16];
       tmem_ld16_issue(lane_base + kColD + c0, ra);
       tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
@@ -191,32 +204,71 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
           for (int j = 0; j < 4; ++j) hg[(size_t)(8 * cq + 4 * half + j) * p.rows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
         }
       }
-      if (r < nrows) reinterpret_cast<uint32_t*>(p.rec + dst_row * kRowRec)[4 + 4 * layer + cq] = mask;   // ReLU mask of this layer
-      if (image_groups_pending == 2 - layer) {   // W2 before the layer-2 MMAs, W3 before the head's
-        mbar_wait(bar + 3 + layer, 0);
-        image_groups_pending = 1 - layer;
-      }
+      if (r < nrows) reinterpret_cast<uint32_t*>(p.rec + dst_row * kRowRec)[4 + cq] = mask;   // ReLU mask of H1
+      if (image_groups_pending == 1) { mbar_wait(bar + 3, 0); image_groups_pending = 0; }   // W2
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncthreads();
+      TSG(g_ts_fwd, 5 + 6 * ts_tile);
       if (t == 0) {
         tc_fence_after();
-        if (layer == 0) issue_kmajor<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
-        else issue_kmajor<kHidden / 8, kHeadRows, kHeadPanelBytes>(tmem, kColDHead, smem_base + kOffW3Hi, smem_base + kOffW3Lo, kHidden / 8);
+        issue_kmajor<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
         mma_commit(bar);
       }
+      // the next (lower) tile's rows, requested under the layer-2 MMAs (the longest stretch in which the CUDA cores idle); the episode index they
+      // hang off was requested at the top of this tile
+      if (has_next) fetch_b(key_nxt, nxt);
       mbar_wait(bar, parity); parity ^= 1;
       tc_fence_after();
+      TSG(g_ts_fwd, 6 + 6 * ts_tile);
+    }
+    // ---- layer-2 epilogue: H2 (FP32, chunk-major) + its mask -> global; head on the CUDA cores against the FP32 copy of W3 (packed FP32: even and
+    // odd columns accumulate in the two halves of a register pair); partial sums of column quarters 1..3 -> shared --------------------------------
+    float q[kOutPad];
+    {
+      uint32_t ra[16], rb[16];
+      tmem_ld16_issue(lane_base + kColD + c0, ra);
+      tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
+      tmem_ld_wait(ra);
+      tmem_ld_wait(rb);
+      float2 q2[kOutPad];
+#pragma unroll
+      for (int a = 0; a < kOutPad; ++a) q2[a] = make_float2(0.f, 0.f);
+      uint32_t mask = 0;
+      float4* hg = reinterpret_cast<float4*>(p.h2g) + dst_row;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t (&acc)[16] = g < 4 ? ra : rb;
+        const int o = 4 * (g & 3);
+        const float4 bb = *reinterpret_cast<const float4*>(b2 + c0 + 4 * g);
+        float2 h01 = __fadd2_rn(make_float2(__uint_as_float(acc[o]), __uint_as_float(acc[o + 1])), make_float2(bb.x, bb.y));
+        float2 h23 = __fadd2_rn(make_float2(__uint_as_float(acc[o + 2]), __uint_as_float(acc[o + 3])), make_float2(bb.z, bb.w));
+        h01.x = fmaxf(h01.x, 0.f); h01.y = fmaxf(h01.y, 0.f); h23.x = fmaxf(h23.x, 0.f); h23.y = fmaxf(h23.y, 0.f);
+        mask |= ((h01.x > 0.f ? 1u : 0u) | (h01.y > 0.f ? 2u : 0u) | (h23.x > 0.f ? 4u : 0u) | (h23.y > 0.f ? 8u : 0u)) << (4 * g);
+        if (r < nrows) hg[(size_t)(8 * cq + g) * p.rows] = make_float4(h01.x, h01.y, h23.x, h23.y);
+#pragma unroll
+        for (int a = 0; a < kOutPad; ++a) {
+          if (a < A) {
+            const float4 w = w3f[a * (kHidden / 4) + (c0 >> 2) + g];
+            q2[a] = __ffma2_rn(h23, make_float2(w.z, w.w), __ffma2_rn(h01, make_float2(w.x, w.y), q2[a]));
+          }
+        }
+      }
+      if (r < nrows) reinterpret_cast<uint32_t*>(p.rec + dst_row * kRowRec)[8 + cq] = mask;   // ReLU mask of H2
+#pragma unroll
+      for (int a = 0; a < kOutPad; ++a) q[a] = q2[a].x + q2[a].y;
+      if (cq > 0) {
+        float4* pp = reinterpret_cast<float4*>(part + ((size_t)(cq - 1) * kTileRows + r) * kOutPad);
+        pp[0] = make_float4(q[0], q[1], q[2], q[3]); pp[1] = make_float4(q[4], q[5], q[6], q[7]);
+      }
+      named_bar_sync(2 + lq, 128);   // the four warps of this lane quarter; the next tile's partials are written two __syncthreads later
+      TSG(g_ts_fwd, 7 + 6 * ts_tile);
     }
     // ---- outputs of this tile -> shared (next-row exchange), TD head: column quarter 0 (threads 0..127, r == t) ------------
     if (cq == 0) {
-      float q[kOutPad];
-      {
-        float v[16];
-        tmem_ld16(lane_base + kColDHead, v);
 #pragma unroll
-        for (int o = 0; o < kOutPad; ++o) q[o] = o < A ? v[o] + b3[o] : 0.f;
-      }
+      for (int o = 0; o < kOutPad; ++o)
+        q[o] = o < A ? (((q[o] + part[((size_t)0 * kTileRows + r) * kOutPad + o]) + part[((size_t)1 * kTileRows + r) * kOutPad + o]) + part[((size_t)2 * kTileRows + r) * kOutPad + o]) + b3[o] : 0.f;
       *reinterpret_cast<float4*>(qs + r * kOutPad) = make_float4(q[0], q[1], q[2], q[3]);
       *reinterpret_cast<float4*>(qs + r * kOutPad + 4) = make_float4(q[4], q[5], q[6], q[7]);
       if (t == 0) {
@@ -257,8 +309,11 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
         *reinterpret_cast<int2*>(p.rec + dst_row * kRowRec) = make_int2(__float_as_int(g), act);
       }
     }
+    TSG(g_ts_fwd, 8 + 6 * ts_tile);
+    ts_tile += 1;
     cur = nxt;
   }
+  TSG(g_ts_fwd, 29);
   // ---- per-CTA loss statistics (threads 0..127 hold them) ---------------------------------------------------------------
   __syncthreads();
   if (t < kTileRows) { qs[t] = st[0]; qs[kTileRows + t] = st[1]; }
@@ -270,7 +325,9 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
   if (t < 4) p.loss_part[4 * blockIdx.x + t] = t < 2 ? qs[t * kTileRows] : 0.f;
   tc_fence_before();
   __syncthreads();
+  TSG(g_ts_fwd, 30);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  TSG(g_ts_fwd, 31);
 }
 
 // =====================================================================================================================
@@ -289,6 +346,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   if (row_begin >= row_end) { pdl_wait(); return; }
+  TSG(g_ts_dh1, 0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -296,6 +354,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
   if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 2, 1); fence_mbar_init(); }
   pdl_wait();   // nothing above touches global memory
   pdl_launch_dependents();
+  TSG(g_ts_dh1, 1);
   if (t == 0) {  // W2^T image + FP32 W3: TMA bulk copies onto one mbarrier
     mbar_expect_tx(bar + 2, (uint32_t)(kBwdImageBytes + kOutPad * kHidden * 4));
     tma_image_range(smem_u32(smem), p.bwd_images + (size_t)net * kBwdImageBytes, 0, kBwdImageBytes, bar + 2);
@@ -321,10 +380,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  TSG(g_ts_dh1, 2);
+  int ts_tile = 0; (void)ts_tile;
   mbar_wait(bar + 2, 0);   // images have landed (every thread reads the FP32 W3 rows; the tensor core reads W2^T)
   const uint32_t tmem = *tmem_slot, smem_base = smem_u32(smem), lane_base = tmem + ((uint32_t)(32 * lq) << 16);
   uint32_t parity = 0;
   for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
+    TSG(g_ts_dh1, 3 + 4 * ts_tile);
     // dH2[r][j] = g W3[act][j] (H2[r][j] > 0) for this thread's 32 columns -> A operand (hi / lo)
     {
       const float4* wrow = w3f4 + cur.act * (kHidden / 4) + 8 * cq;
@@ -346,6 +408,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     __syncthreads();
+    TSG(g_ts_dh1, 4 + 4 * ts_tile);
     if (t == 0) {
       tc_fence_after();
       // D[r][j1] = sum_{j2} dH2[r][j2] W2[j2][j1]: B = K-major image of W2^T (rows j1, features j2), the forward layers' MMA form
@@ -355,6 +418,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
     if (vr0 + kTileRows < row_end) fetch(vr0 + kTileRows, nxt);
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
+    TSG(g_ts_dh1, 5 + 4 * ts_tile);
     {
       uint32_t ra[16], rb[16];
       tmem_ld16_issue(lane_base + kColD + c0, ra);
@@ -375,10 +439,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
         }
       }
     }
+    TSG(g_ts_dh1, 6 + 4 * ts_tile);
+    ts_tile += 1;
     cur = nxt;
   }
   tc_fence_before();
   __syncthreads();
+  TSG(g_ts_dh1, 31);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -387,19 +454,24 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dh1_kernel(TcTrainParams p) 
 // =====================================================================================================================
 constexpr int kDwProducers = 512;                    // 16 staging warps
 constexpr int kDwThreads = kDwProducers + 32;        // + the MMA-issuing warp
-constexpr int kChunkRows = 16;                       // rows per staged chunk (two 8-row k-steps); two chunk buffers alternate
+constexpr int kChunkRows = 16;                       // rows per staged chunk (two 8-row k-steps)
+#ifndef MARL_DW_BUFS
+#define MARL_DW_BUFS 3
+#endif
+constexpr int kDwBufs = MARL_DW_BUFS;                // depth of the chunk ring (and of the register prefetch): the producers run that many chunks ahead of the tensor core
 constexpr int kChunkPanel = kChunkRows * 128;        // one 32-feature panel of a chunk
 constexpr int kOpBytes = 4 * kChunkPanel;            // a [16 rows][128 features] operand (hi or lo)
 // shared-memory map of one chunk buffer (bytes): dH2 hi|lo, H1 hi (+ ones panel) | lo (+ zero panel), dH1 hi|lo, X hi|lo
 constexpr int kSDh2 = 0, kSH1 = kSDh2 + 2 * kOpBytes, kSDh1 = kSH1 + 2 * (kOpBytes + kChunkPanel), kSX = kSDh1 + 2 * kOpBytes;
 constexpr int kSEnd = kSX + 2 * kChunkPanel;
-constexpr int kDwW3 = 2 * kSEnd;                               // FP32 copy of W3 [8][128]
-constexpr int kDwBars = kDwW3 + kOutPad * kHidden * 4;         // full[2], empty[2], done, TMEM slot
+constexpr int kDwW3 = kDwBufs * kSEnd;                         // FP32 copy of W3 [8][128]
+constexpr int kDwBars = kDwW3 + kOutPad * kHidden * 4;         // full[kDwBufs], empty[kDwBufs], done, TMEM slot
 constexpr int kDwSmemBytes = kDwBars + 64 + 1024;              // + alignment slack
 static_assert(kSEnd % 1024 == 0, "chunk buffers must keep the 1024-byte swizzle alignment");
+static_assert(kDwBufs >= 2 && kDwBufs <= 3 && kDwSmemBytes <= 227 * 1024, "chunk ring: 2 or 3 buffers of 56 KB");
 // epilogue scratch (the chunk buffers are dead by then): dW3 / db3 partials of the four row groups, then one transpose tile per warp
 constexpr int kDwRed3 = 0, kDwRedG = kDwRed3 + 4 * kOutPad * kHidden * 4, kDwTile = kDwRedG + 1024, kDwTileBytes = 32 * 33 * 4;
-static_assert(kDwTile + 16 * kDwTileBytes <= 2 * kSEnd, "epilogue scratch must fit in the chunk buffers");
+static_assert(kDwTile + 16 * kDwTileBytes <= kDwBufs * kSEnd, "epilogue scratch must fit in the chunk buffers");
 // TMEM columns: dW2 | db2 [0,160), dW1 | db1 [160,192)
 constexpr uint32_t kColW2 = 0, kColW1 = 160;
 
@@ -415,10 +487,10 @@ __device__ __forceinline__ void stage4(uint8_t* hi_img, uint8_t* lo_img, int r, 
 __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDwBars);   // [2] chunk buffer staged (16 producer-warp arrivals)
-  uint64_t* empty = full + 2;                                     // [2] chunk buffer consumed by the tensor core (tcgen05.commit)
-  uint64_t* done = full + 4;                                      // every MMA retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 5);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDwBars);   // [kDwBufs] chunk buffer staged (16 producer-warp arrivals)
+  uint64_t* empty = full + kDwBufs;                               // [kDwBufs] chunk buffer consumed by the tensor core (tcgen05.commit)
+  uint64_t* done = full + 2 * kDwBufs;                            // every MMA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kDwBufs + 1);
   const float4* w3f4 = reinterpret_cast<const float4*>(smem + kDwW3);
   // staging: warp = (4-row group, 32-feature panel), lane = (float4 column within the panel, row within the group): shared-memory
   // stores of the swizzled MN-major image stay conflict-free and every global load instruction reads eight 64-byte segments
@@ -432,16 +504,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
     for (int i = t; i < p.lay.P; i += kDwThreads) gs[i] = 0.f;
     return;
   }
+  TSG(g_ts_dw, 0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) {
-    mbar_init(full, kDwProducers / 32); mbar_init(full + 1, kDwProducers / 32);   // one arrival per producer warp
-    mbar_init(empty, 1); mbar_init(empty + 1, 1); mbar_init(done, 1);
+    for (int b = 0; b < kDwBufs; ++b) { mbar_init(full + b, kDwProducers / 32); mbar_init(empty + b, 1); }   // one arrival per producer warp
+    mbar_init(done, 1);
   }
-  // constant panels of both buffers: ones column (n = 128) behind H1 hi, zeros behind H1 lo; W3 copy
-  for (int i = t; i < 2 * (kChunkPanel / 4); i += kDwThreads) {
+  // constant panels of every buffer: ones column (n = 128) behind H1 hi, zeros behind H1 lo; W3 copy
+  for (int i = t; i < kDwBufs * (kChunkPanel / 4); i += kDwThreads) {
     uint8_t* bufp = smem + (i / (kChunkPanel / 4)) * kSEnd;
     const int w = i % (kChunkPanel / 4);
     reinterpret_cast<float*>(bufp + kSH1 + kOpBytes)[w] = 0.f;
@@ -449,12 +522,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   }
   pdl_wait();   // nothing above touches global memory
   pdl_launch_dependents();
+  TSG(g_ts_dw, 1);
   {
     const float4* w3src = reinterpret_cast<const float4*>(p.images + (size_t)net * kImageBytes + kOffW3F);
     for (int i = t; i < kOutPad * kHidden / 4; i += kDwThreads) reinterpret_cast<float4*>(smem + kDwW3)[i] = w3src[i];
   }
   __syncthreads();
-  if (t < 2 * kChunkRows) *reinterpret_cast<float*>(smem + (t / kChunkRows) * kSEnd + kSH1 + kOpBytes + mn_offset(t % kChunkRows, 0, kChunkPanel)) = 1.0f;
+  if (t < kDwBufs * kChunkRows) *reinterpret_cast<float*>(smem + (t / kChunkRows) * kSEnd + kSH1 + kOpBytes + mn_offset(t % kChunkRows, 0, kChunkPanel)) = 1.0f;
   const int D = p.src.D, A = p.lay.out;
   const int n_chunks = (row_end - row_begin + kChunkRows - 1) / kChunkRows, rpa = p.plan.units_per_agent * p.plan.unit_rows;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -462,6 +536,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot, sb = smem_u32(smem);
+  TSG(g_ts_dw, 2);
 
   float acc3[kOutPad][4];   // dW3[a][4 c4 .. 4 c4 + 3] over this thread's rows; gacc: db3 (used where c4 == 0)
   float gacc[kOutPad];
@@ -517,32 +592,32 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
         acc3[a][2] = fmaf(ga, pre.h2.z, acc3[a][2]); acc3[a][3] = fmaf(ga, pre.h2.w, acc3[a][3]);
       }
     };
-    Pre pre0, pre1;
-    issue_loads(0, pre0);
-    issue_loads(1, pre1);   // past the end: zeros, no loads
-    for (int c = 0; c < n_chunks; c += 2) {
-      // even chunk -> buffer 0 (its previous user, chunk c - 2, must have been consumed by the tensor core)
-      if (c >= 2) mbar_wait(empty, ((c >> 1) - 1) & 1);
-      stage(smem, pre0);
-      issue_loads(c + 2, pre0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full);   // 16 arrivals per chunk instead of 512 serialised shared-memory atomics
-      if (c + 1 < n_chunks) {
-        if (c >= 2) mbar_wait(empty + 1, ((c >> 1) - 1) & 1);
-        stage(smem + kSEnd, pre1);
-        issue_loads(c + 3, pre1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full + 1);
+    // register prefetch two chunks ahead (global / L2 latency), shared-memory ring kDwBufs deep (tensor-core + barrier latency); the loop is
+    // unrolled over lcm(2, kDwBufs) chunks so that both indices are compile-time constants (pre[] stays in registers)
+    constexpr int kUnroll = 2 * kDwBufs / (kDwBufs % 2 == 0 ? 2 : 1);
+    Pre pre[2];
+    issue_loads(0, pre[0]);
+    issue_loads(1, pre[1]);   // past the end: zeros, no loads
+    for (int c0 = 0; c0 < n_chunks; c0 += kUnroll) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int c = c0 + u, b = u % kDwBufs, use = c0 / kDwBufs + u / kDwBufs;   // chunk c is the use-th user of buffer b
+        if (c < n_chunks) {
+          if ((c & 1) == 0) TSG(g_ts_dw, 3 + (c >> 1));   // every second chunk (at most 24 chunks: slots 3..14)
+          if (use > 0) mbar_wait(empty + b, (use - 1) & 1);   // its previous user (chunk c - kDwBufs) has been consumed by the tensor core
+          stage(smem + b * kSEnd, pre[u & 1]);
+          issue_loads(c + 2, pre[u & 1]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full + b);   // 16 arrivals per chunk instead of 512 serialised shared-memory atomics
+        }
       }
     }
   } else {
     // ---- MMA warp: per chunk 12 MMAs (3xTF32 terms x 2 k-steps x 2 GEMMs), then a commit that frees the buffer ----------------
     const uint32_t id_w2 = idesc_tf32_major(160, 1, 1), id_w1 = idesc_tf32_major(32, 1, 1);
-    for (int c = 0; c < n_chunks; ++c) {
-      const int b = c & 1;
-      mbar_wait(full + b, (c >> 1) & 1);
+    for (int c = 0, b = 0, round = 0; c < n_chunks; ++c) {
+      mbar_wait(full + b, round & 1);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t base = sb + b * kSEnd;
@@ -565,10 +640,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
         if (c == n_chunks - 1) mma_commit(done);   // completes when every MMA issued above has
       }
       __syncwarp();
+      if (++b == kDwBufs) { b = 0; ++round; }
     }
   }
+  TSG(g_ts_dw, 24);
   mbar_wait(done, 0);
   tc_fence_after();
+  TSG(g_ts_dw, 25);
   __syncthreads();   // every producer is past its last use of the chunk buffers: they become epilogue scratch
   // ---- dW3 / db3: sum over the four rows of a lane group (shuffles), then over the four row groups (fixed order) ------------
   float* red3 = reinterpret_cast<float*>(smem + kDwRed3);   // [4 row groups][8][128]
@@ -601,6 +679,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   for (int i = t; i < A * kHidden; i += kDwThreads)
     gs[p.lay.w3 + i] = (red3[i] + red3[kOutPad * kHidden + i]) + (red3[2 * kOutPad * kHidden + i] + red3[3 * kOutPad * kHidden + i]);
   if (t < A) gs[p.lay.b3 + t] = (redg[t] + redg[kOutPad + t]) + (redg[2 * kOutPad + t] + redg[3 * kOutPad + t]);
+  TSG(g_ts_dw, 26);
   // ---- flush the TMEM accumulators: lane j of lane quarter lq owns output feature j; each warp transposes its 32 x 32 block of
   // dW2 through shared memory so that every store instruction writes one 128-byte row segment ------------------------------------
   if (producer) {
@@ -635,6 +714,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_dw_kernel(TcTrainParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  TSG(g_ts_dw, 31);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
@@ -660,11 +740,11 @@ int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_
   p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
   p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
-  const bool pingpong = tc_pingpong_enabled() && p.src.mode == 1;   // two-accumulator kernels (tc_train2.cu)
-  if (pingpong) { if (int rc = launch_tc_dqn_fwd2(p, grid, st)) return rc; }
+  const bool pp_fwd = tc_pingpong_enabled(0) && p.src.mode == 1, pp_dh1 = tc_pingpong_enabled(1) && p.src.mode == 1;   // two-accumulator kernels (tc_train2.cu)
+  if (pp_fwd) { if (int rc = launch_tc_dqn_fwd2(p, grid, st)) return rc; }
   else MARL_CUDA_TRY(launch_pdl(tc_dqn_fwd_kernel, dim3(grid), dim3(kTrThreads), kFwdTrainSmem, st, p));
   if (between) MARL_CUDA_TRY(cudaEventRecord(between[0], st));
-  if (pingpong) { if (int rc = launch_tc_dh12(p, grid, st)) return rc; }
+  if (pp_dh1) { if (int rc = launch_tc_dh12(p, grid, st)) return rc; }
   else MARL_CUDA_TRY(launch_pdl(tc_dh1_kernel, dim3(grid), dim3(kTrThreads), kDh1Smem, st, p));
   if (between) MARL_CUDA_TRY(cudaEventRecord(between[1], st));
   MARL_CUDA_TRY(launch_pdl(tc_dw_kernel, dim3(grid), dim3(kDwThreads), kDwSmemBytes, st, p));

@@ -383,6 +383,8 @@ constexpr int kH2Bars = kH2Rec + 4 * kTileRows * 48;
 constexpr int kH2Smem = kH2Bars + 64 + 1024;
 static_assert(kH2Smem <= 227 * 1024, "ping-pong dH1: shared-memory map");
 
+TSG_DEFINE(g_ts_dh12)
+TSG_GETTER(tsg_dh12, g_ts_dh12)
 __global__ void __launch_bounds__(kT2Threads, 1) tc_dh12_kernel(TcTrainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -393,6 +395,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) tc_dh12_kernel(TcTrainParams p)
   int net, row_begin, row_end;
   cta_rows(p.plan, net, row_begin, row_end);
   if (row_begin >= row_end) { pdl_wait(); return; }
+  TSG(g_ts_dh12, 0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -400,6 +403,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) tc_dh12_kernel(TcTrainParams p)
   if (t == 0) { mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); mbar_init(bar + 4, kTrThreads / 32); mbar_init(bar + 6, kT2Loaders / 32); mbar_init(bar + 7, kT2Loaders / 32); fence_mbar_init(); }
   pdl_wait();   // nothing above touches global memory
   pdl_launch_dependents();
+  TSG(g_ts_dh12, 1);
   const uint32_t smem_base = smem_u32(smem);
   if (t == 0) {
     mbar_expect_tx(bar + 2, (uint32_t)(kBwdImageBytes + kOutPad * kHidden * 4));
@@ -470,11 +474,13 @@ __global__ void __launch_bounds__(kT2Threads, 1) tc_dh12_kernel(TcTrainParams p)
     const int lq = warp & 3, cq = warp >> 2, r = 32 * lq + lane, c0 = 32 * cq;
     const uint32_t lane_base = tmem + ((uint32_t)(32 * lq) << 16);
     const float4* w3f4 = reinterpret_cast<const float4*>(smem + kH2W3);
+    TSG(g_ts_dh12, 2);
     mbar_wait(bar + 2, 0);   // FP32 W3 rows
     uint32_t ph = 0;
     for (int k = 0; k <= n_tiles; ++k) {
       // ---- dH2 of tile k for this thread's 32 columns, FP32, in registers (the MMAs of tile k - 1 may still be reading the A columns) ----------------
       float v[32];
+      TSG(g_ts_dh12, 3 + 4 * k);
       if (k < n_tiles) {
         mbar_wait(bar + 6 + (k & 1), (uint32_t)(k >> 1) & 1u);   // the records of tile k are in shared memory
         const uint32_t* pr = recs + ((size_t)(k & 3) * kTileRows + r) * 12;
@@ -490,7 +496,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) tc_dh12_kernel(TcTrainParams p)
           v[4 * j + 2] = (m & 4u) ? g * w.z : 0.f; v[4 * j + 3] = (m & 8u) ? g * w.w : 0.f;
         }
       }
+      TSG(g_ts_dh12, 4 + 4 * k);
       if (k > 0) { mbar_wait(bar + 1, ph); ph ^= 1; tc_fence_after(); }   // MMAs of tile k - 1 retired: A free, D_{(k-1)&1} holds its result
+      TSG(g_ts_dh12, 5 + 4 * k);
       if (k < n_tiles) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -515,6 +523,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) tc_dh12_kernel(TcTrainParams p)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + 4);
       }
+      TSG(g_ts_dh12, 6 + 4 * k);
       // ---- dH1 of tile k - 1: mask with relu'(H1) and store (chunk-major) ------------------------------------------------------------------------------
       if (k > 0) {
         const uint32_t* pr = recs + ((size_t)((k - 1) & 3) * kTileRows + r) * 12;
@@ -537,6 +546,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) tc_dh12_kernel(TcTrainParams p)
   }
   tc_fence_before();
   __syncthreads();
+  TSG(g_ts_dh12, 31);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 

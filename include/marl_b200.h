@@ -35,6 +35,10 @@ const char* marl_last_error(void);
 /* Process-wide options: "tensor_core_forward" 1 (default) = forward-only passes on tcgen05 with the 3xTF32 split, 0 = FP32 FFMA;
  * "tensor_core_backward" 1 = the DQN-family training pass runs as the three-kernel tcgen05 pipeline (tc_train.cu), 0 = fused FP32 kernel. */
 int marl_set_option(const char* name, int32_t value);
+/* "tensor_core_pingpong": bit mask of the tensor-core kernels that keep two accumulators in TMEM (bit 0 forward kernels, bit 1 dH1 kernel; default 2).
+ * Profiling builds (-DMARL_TC_TIMESTAMPS): timeline probes of kernel `which` as uint64 [160 CTAs][32 slots][globaltimer ns, clock64] into HOST
+ * memory; product builds return MARL_EINVAL. */
+int marl_debug_timestamps(int32_t which, uint64_t* out);
 
 /* ------------------------------------------------------------------------------------------------------
  * Level-Based Foraging, E environments per handle, one transition of all of them per launch.

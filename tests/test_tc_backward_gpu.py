@@ -30,7 +30,7 @@ def _restore():
     yield
     _opt(b"tensor_core_backward", True)   # the library defaults
     _opt(b"tensor_core_forward", True)
-    _opt(b"tensor_core_pingpong", True)
+    _opt(b"tensor_core_pingpong", 2)      # bit mask: forward kernels | dH1 kernel; default: dH1 only
 
 
 def _store(rng, cap, N, T, D, coop):
@@ -75,9 +75,9 @@ def test_tc_backward_matches_ffma_and_oracle(mixer, N, D, T, B, sharing):
     n = m.n_params
     scale = max(1.0, float(np.abs(want["grad"].numpy()).max()))
     grads = {}
-    for tc in (0, 2, 1):   # 0: fused FP32 kernel; 2: tensor-core pipeline, one tile at a time; 1: tensor-core pipeline, two accumulators (default; applied below)
+    for tc in (0, 2, 3, 1):   # 0: fused FP32 kernel; tensor-core pipeline -- 2: one tile at a time, 3: two accumulators everywhere, 1: the default (two accumulators in the dH1 kernel; applied below)
         _opt(b"tensor_core_backward", int(tc > 0))
-        _opt(b"tensor_core_pingpong", int(tc == 1))
+        _opt(b"tensor_core_pingpong", {0: 0, 2: 0, 3: 3, 1: 2}[tc])
         m.update_grads(ts, idx_d)
         torch.cuda.synchronize()
         g = m.grad.cpu().numpy()
@@ -85,7 +85,7 @@ def test_tc_backward_matches_ffma_and_oracle(mixer, N, D, T, B, sharing):
         assert abs(g[n] / g[n + 1] - want["loss"]) <= 1e-5 * max(1.0, abs(want["loss"])), (tc, g[n] / g[n + 1], want["loss"])
         err = np.abs(grads[tc] - want["grad"].numpy()).max() / scale
         assert err < 1e-5, (tc, err)
-    assert np.abs(grads[0] - grads[1]).max() / scale < 1e-5 and np.abs(grads[0] - grads[2]).max() / scale < 1e-5
+    assert all(np.abs(grads[0] - grads[k]).max() / scale < 1e-5 for k in (1, 2, 3))
     met = m.update_apply().cpu().numpy()  # applies the tensor-core gradients
     d = np.abs(m.theta.cpu().numpy() - st.theta.numpy())
     assert np.quantile(d, 0.999) < 1e-5 and abs(met[0] - want["loss"]) <= 1e-5 * max(1.0, abs(want["loss"]))

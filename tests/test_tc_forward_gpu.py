@@ -16,7 +16,7 @@ def _space(shape=None, n=None):
     return types.SimpleNamespace(shape=shape, n=n)
 
 
-def _set_tc(on: bool, pingpong: bool = True):
+def _set_tc(on: bool, pingpong: int = 2):   # pingpong: the library's bit mask (bit 0 = forward kernels; default 2 = dH1 kernel only)
     from codebase_b200 import _native as nat
 
     nat.check(nat.lib().marl_set_option(b"tensor_core_forward", C.c_int32(int(on))), "marl_set_option")
@@ -26,10 +26,10 @@ def _set_tc(on: bool, pingpong: bool = True):
 @pytest.fixture(autouse=True)
 def _restore():
     yield
-    _set_tc(True, True)
+    _set_tc(True, 2)
 
 
-@pytest.mark.parametrize("pingpong", [True, False])
+@pytest.mark.parametrize("pingpong", [3, 0])
 @pytest.mark.parametrize("n_agents,D,sharing,E", [(2, 15, False, 4096), (2, 15, True, 1000), (4, 27, False, 333), (3, 32, [0, 1, 0], 129), (2, 15, False, 1),
                                                   (2, 15, False, 40000), (1, 9, False, 20000)])   # the last two: several tiles per CTA (the two-accumulator pipeline proper)
 def test_dense_forward_tc_vs_ffma_vs_oracle(n_agents, D, sharing, E, pingpong):
