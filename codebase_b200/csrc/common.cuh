@@ -95,5 +95,6 @@ int check_device(int device);
 int tc_forward_enabled();
 int tc_backward_enabled();
 int tc_pingpong_enabled(int which);   // 0: forward kernels, 1: dH1 kernel
+int tc_onchip_enabled();
 
 }  // namespace marl

@@ -38,6 +38,10 @@ static int env_int(const char* name, int dflt) { const char* v = getenv(name); r
 // two-accumulator forward kernels do not amortise their pipeline fill (measured slower than the one-tile kernels), the dH1 kernel does.
 static int g_tc_forward = 1, g_tc_backward = 1, g_tc_pingpong = env_int("MARL_TC_PINGPONG", 2);   // the environment variable only moves the default
 int tc_pingpong_enabled(int which) { return (g_tc_pingpong >> which) & 1; }
+static int g_tc_onchip = env_int("MARL_TC_ONCHIP", 1);
+int tc_onchip_enabled() { return g_tc_onchip; }
+static unsigned long long* g_dbg_progress = nullptr;
+unsigned long long* tc_debug_progress_ptr() { return g_dbg_progress; }
 int tc_forward_enabled() { return g_tc_forward; }
 int tc_backward_enabled() { return g_tc_backward; }
 
@@ -52,6 +56,9 @@ int marl_set_option(const char* name, int32_t value) {
   /* bit mask of the tensor-core kernels that use two accumulator buffers in TMEM (the epilogue of one 128-row tile runs under the MMAs of the
    * next): bit 0 = forward kernels, bit 1 = dH1 kernel; default 2.  0: one tile at a time everywhere */
   if (name && strcmp(name, "tensor_core_pingpong") == 0) { marl::g_tc_pingpong = value & 3; return MARL_OK; }
+  /* 1 (default): the training pass keeps H1 / H2 / dH1 on chip (tc_train3.cu: 192 bytes per row cross kernels); 0: the previous pipeline, which
+   * streams them through global memory (tc_train.cu) */
+  if (name && strcmp(name, "tensor_core_onchip") == 0) { marl::g_tc_onchip = value ? 1 : 0; return MARL_OK; }
   marl::set_error("marl_set_option: unknown option '%s'", name ? name : "(null)");
   return MARL_EINVAL;
 }
@@ -64,11 +71,14 @@ int marl_debug_timestamps(int32_t which, uint64_t* out) {
   switch (which) {
     case 0: rc = marl::tsg_forward(o); break; case 1: rc = marl::tsg_fwd(o); break; case 2: rc = marl::tsg_dh1(o); break;
     case 3: rc = marl::tsg_dw(o); break; case 4: rc = marl::tsg_adam(o); break; case 5: rc = marl::tsg_dh12(o); break;
+    case 6: rc = marl::tsg_fwd3(o); break; case 7: rc = marl::tsg_dh1w1(o); break; case 8: rc = marl::tsg_dw2(o); break;
     default: break;
   }
   if (rc != 0) { marl::set_error("marl_debug_timestamps: kernel %d has no probes in this build (build with -DMARL_TC_TIMESTAMPS)", (int)which); return MARL_EINVAL; }
   return MARL_OK;
 }
+/* Profiling builds: host-mapped buffer (cudaHostAlloc'd by the caller, uint64 [3][160][32]) that the on-chip training kernels mark their progress in. */
+int marl_debug_progress(uint64_t* mapped) { marl::g_dbg_progress = reinterpret_cast<unsigned long long*>(mapped); return MARL_OK; }
 int marl_version(void) { return MARL_ABI_VERSION; }
 const char* marl_last_error(void) { return marl::g_err; }
 }

@@ -86,13 +86,19 @@ constexpr int kTsgCtas = 160, kTsgSlots = 32;
 #define TSG(name, slot) do { if (threadIdx.x == 0 && blockIdx.x < kTsgCtas && (slot) < kTsgSlots) { unsigned long long g_; \
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); name[blockIdx.x][(slot)][0] = g_; name[blockIdx.x][(slot)][1] = (unsigned long long)clock64(); } } while (0)
 #define TSG_GETTER(fn, name) int fn(unsigned long long* out) { return cudaMemcpyFromSymbol(out, name, sizeof(name)) == cudaSuccess ? 0 : -1; }
+// the same probe plus a progress mark per WARP in host-mapped memory (dbg: [3 kernels][160 CTAs][32 warps], slot + 1 of the last probe the warp
+// passed): readable from the host while a kernel hangs (tools/debug_hang.py)
+#define TSGP(name, dbg, kid, slot) do { TSG(name, slot); if ((dbg) != nullptr && (threadIdx.x & 31) == 0 && blockIdx.x < kTsgCtas) { \
+  *reinterpret_cast<volatile unsigned long long*>((dbg) + ((kid) * kTsgCtas + blockIdx.x) * 32 + (threadIdx.x >> 5)) = (unsigned long long)((slot) + 1); } } while (0)
 #else
+#define TSGP(name, dbg, kid, slot)
 #define TSG_DEFINE(name)
 #define TSG(name, slot)
 #define TSG_GETTER(fn, name) int fn(unsigned long long*) { return -1; }
 #endif
 int tsg_forward(unsigned long long* out); int tsg_fwd(unsigned long long* out); int tsg_dh1(unsigned long long* out); int tsg_dw(unsigned long long* out);
 int tsg_dh12(unsigned long long* out); int tsg_adam(unsigned long long* out);
+int tsg_fwd3(unsigned long long* out); int tsg_dh1w1(unsigned long long* out); int tsg_dw2(unsigned long long* out);
 
 // dynamic shared memory rounded up to 1024 bytes (swizzle atoms), keeping the pointer in the shared address space so that the
 // compiler emits LDS / STS rather than generic loads and stores
@@ -250,9 +256,13 @@ struct TcTrainParams {
                               // kernel reads them without chasing the episode index again
   const float* tq; const float* td_ext; float gamma; int double_q;
   float* scratch; int scratch_pitch; float* loss_part;
+  unsigned long long* dbg;    // profiling builds: host-mapped progress marks (NULL otherwise)
 };
+unsigned long long* tc_debug_progress_ptr();   // core.cu
 
 int tc_train2_init();
+int tc_train3_init();
+int launch_tc_dqn_train3(const TcTrainParams& p, int grid, cudaStream_t st, cudaEvent_t* between);   // tc_train3.cu: activations stay on chip
 int launch_tc_dqn_fwd2(const TcTrainParams& p, int grid, cudaStream_t st);
 int launch_tc_dh12(const TcTrainParams& p, int grid, cudaStream_t st);
 

@@ -728,7 +728,8 @@ int tc_train_init() {
   MARL_CUDA_TRY(cudaFuncSetAttribute(tc_dqn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdTrainSmem));
   MARL_CUDA_TRY(cudaFuncSetAttribute(tc_dh1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDh1Smem));
   MARL_CUDA_TRY(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
-  return tc_train2_init();
+  if (int rc = tc_train2_init()) return rc;
+  return tc_train3_init();
 }
 
 // all three kernels walk the same episode-aligned row split, so the per-CTA partials line up with ReduceParams::cta_begin
@@ -740,6 +741,8 @@ int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_
   p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
   p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
+  p.dbg = tc_debug_progress_ptr();
+  if (tc_onchip_enabled()) return launch_tc_dqn_train3(p, grid, st, between);
   const bool pp_fwd = tc_pingpong_enabled(0) && p.src.mode == 1, pp_dh1 = tc_pingpong_enabled(1) && p.src.mode == 1;   // two-accumulator kernels (tc_train2.cu)
   if (pp_fwd) { if (int rc = launch_tc_dqn_fwd2(p, grid, st)) return rc; }
   else MARL_CUDA_TRY(launch_pdl(tc_dqn_fwd_kernel, dim3(grid), dim3(kTrThreads), kFwdTrainSmem, st, p));

@@ -39,6 +39,9 @@ int marl_set_option(const char* name, int32_t value);
  * Profiling builds (-DMARL_TC_TIMESTAMPS): timeline probes of kernel `which` as uint64 [160 CTAs][32 slots][globaltimer ns, clock64] into HOST
  * memory; product builds return MARL_EINVAL. */
 int marl_debug_timestamps(int32_t which, uint64_t* out);
+/* Profiling builds: `mapped` = host-mapped (pinned, device-visible) uint64 [3][160][32]: the on-chip training kernels store, per kernel / CTA / warp,
+ * 1 + the last probe slot the warp passed -- readable from the host while a kernel hangs.  NULL switches it off. */
+int marl_debug_progress(uint64_t* mapped);
 
 /* ------------------------------------------------------------------------------------------------------
  * Level-Based Foraging, E environments per handle, one transition of all of them per launch.

@@ -76,8 +76,16 @@ def init_flat(n_nets, in_dim, out_dim, orthogonal=True, generator=None):
     return torch.cat(parts).float()
 
 
+_TAPS = None   # kink_risk(): hidden pre-/post-activations of the differentiated (online) passes
+
+
 def mlp(flat_net, x, in_dim, out_dim):
     w1, b1, w2, b2, w3, b3 = split_net(flat_net, in_dim, out_dim)
+    if _TAPS is not None and flat_net.requires_grad:
+        z1 = F.linear(x, w1, b1); h1 = F.relu(z1); h1.retain_grad()
+        z2 = F.linear(h1, w2, b2); h2 = F.relu(z2); h2.retain_grad()
+        _TAPS.append((z1, h1, x)); _TAPS.append((z2, h2, h1))
+        return F.linear(h2, w3, b3)
     return F.linear(F.relu(F.linear(F.relu(F.linear(x, w1, b1)), w2, b2)), w3, b3)
 
 
@@ -167,6 +175,32 @@ def double_q_margin(st: DqnState, batch, hp: DqnHP):
         gap = (top2[..., 0] - top2[..., 1]) / top2[..., 0].abs().clamp_min(1.0)
         mask = batch["filled"].unsqueeze(0).expand_as(gap) > 0
         return float(gap[mask].min()) if bool(mask.any()) else float("inf")
+
+
+def kink_risk(loss_fn, theta, near=2e-6):
+    """ReLU is the learners' other discontinuity (next to the double-Q argmax): a hidden pre-activation z within the implementations' ~1e-6
+    agreement of zero may be "on" in one and "off" in the other, which moves the gradient by dL/dh[r][j] x (the unit's input row) -- not a defect.
+    Returns the largest such potential move over all hidden units with |z| < near (0 when there is none): loss_fn(theta) -> scalar loss."""
+    global _TAPS
+    _TAPS = []
+    try:
+        th = theta.clone().requires_grad_(True)
+        loss_fn(th).backward()
+        risk = 0.0
+        for z, h, inp in _TAPS:
+            if h.grad is None:
+                continue
+            m = (z.detach().abs() < near) & (z.detach() != 0)
+            if bool(m.any()):
+                scale_in = inp.detach().abs().amax(dim=-1, keepdim=True).clamp_min(1.0).expand_as(z)
+                risk = max(risk, float((h.grad.abs() * scale_in)[m].max()))
+        return risk
+    finally:
+        _TAPS = None
+
+
+def dqn_kink_risk(st: DqnState, batch, hp: DqnHP):
+    return kink_risk(lambda th: dqn_loss(th, st.theta_tgt, st.agent_net, st.in_dim, st.out_dim, batch, hp), st.theta)
 
 
 def dqn_update(st: DqnState, batch, hp: DqnHP):

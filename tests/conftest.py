@@ -31,10 +31,20 @@ def _seed_everything(request):
     import numpy as np
 
     random.seed(12345); np.random.seed(12345)
+    threads = None
     try:
         import torch
 
         torch.manual_seed(12345)
+        threads = torch.get_num_threads()
     except ImportError:
         pass
     yield
+    # run.main pins torch to one thread like the reference (run.py:29).  The CPU oracle's float32 reductions (bias gradients: sums over ~13k rows)
+    # are sequential in that mode and carry ~1e-5 of rounding error of their own, which made an oracle comparison that ran AFTER a driver test fail
+    # at 1.5e-5 while passing (7e-7) on its own: the thread count is process state and must not leak between tests.
+    if threads is not None:
+        import torch
+
+        if torch.get_num_threads() != threads:
+            torch.set_num_threads(threads)

@@ -8,12 +8,31 @@ TIE = 2e-5   # relative gap of the two best online Q-values under which the doub
 
 
 class NearTie(Exception):
-    """The seeded case has a double-Q argmax margin below TIE: comparing against the oracle would be a coin toss on the selected target action."""
+    """The seeded case sits on a discontinuity of the loss gradient -- a double-Q argmax margin below TIE, or a ReLU unit at its kink with a visible
+    gradient share: comparing against the oracle would be a coin toss."""
 
 
 def check_margin(lr, st, batch, hp):
     if lr.double_q_margin(st, batch, hp) < TIE:
         raise NearTie()
+
+
+def assert_grad_close(lr, st, batch, hp, got, want, tol=1e-5, what=""):
+    """max |got - want| <= tol x max(1, max |want|).  A mismatch that a single ReLU unit sitting on its kink explains is a NearTie, not a failure: a
+    hidden pre-activation within ~1e-6 of zero may be "on" in one implementation and "off" in the other (they agree to ~5e-7), which moves the
+    gradient by up to dL/dh x (the unit's input row) = oracle.learner_ref.dqn_kink_risk -- e.g. 1.3e-3 for VDN at batch 16, T = 127, where the
+    defect-free kernels of two consecutive builds "failed" this way.  The excuse only covers mismatches up to twice that bound."""
+    import numpy as np
+
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = max(1.0, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max())
+    if err <= tol * scale:
+        return
+    risk = lr.dqn_kink_risk(st, batch, hp)
+    if risk >= 0.5 * err:
+        raise NearTie()
+    raise AssertionError(f"{what} max abs error {err:.3e} > {tol:g} x {scale:.3g} (largest ReLU-kink move of this case: {risk:.3e})")
 
 
 def redraw_on_near_tie(fn):

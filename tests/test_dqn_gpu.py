@@ -10,6 +10,7 @@ import torch
 
 from oracle import learner_ref as lr
 from oracle import policy_ref
+from tests.helpers import NearTie, assert_grad_close
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -141,12 +142,15 @@ def _three_glued_updates(mixer, sharing, B, n_agents):
         batch = lr.batch_from_store(store, idx)
         if lr.double_q_margin(st, batch, hp) < TIE:
             return "near-tie"   # the comparison would be a coin toss on which target action is selected
+        st_before = lr.DqnState(st.theta.clone(), st.theta_tgt.clone(), st.agent_net, D, A)
         want = lr.dqn_update(st, batch, hp)
         ts = _store_to_device(store, m.device)
         m.update_grads(ts, torch.tensor(idx, device="cuda"))
         gr = m.grad.cpu().numpy()
-        scale = max(1.0, float(np.abs(want["grad"].numpy()).max()))
-        _close(gr[:m.n_params] / gr[m.n_params + 1] / scale, want["grad"].numpy() / scale)
+        try:   # ... or when a ReLU unit on its kink explains a mismatch (tests/helpers.py)
+            assert_grad_close(lr, st_before, batch, hp, gr[:m.n_params] / gr[m.n_params + 1], want["grad"].numpy())
+        except NearTie:
+            return "near-tie"
         _close_scaled(_clipped(gr[:m.n_params] / gr[m.n_params + 1], hp.grad_clip), want["grad_clipped"].numpy())
         met = m.update_apply().cpu().numpy()
         _close(met[0], want["loss"]); _close(met[1], want["grad_norm"], rtol=1e-4)

@@ -9,7 +9,7 @@ import torch
 
 from oracle import learner_ref as lr
 
-from tests.helpers import check_margin, redraw_on_near_tie
+from tests.helpers import check_margin, redraw_on_near_tie, assert_grad_close
 
 pytestmark = pytest.mark.gpu
 A = 6
@@ -31,6 +31,7 @@ def _restore():
     _opt(b"tensor_core_backward", True)   # the library defaults
     _opt(b"tensor_core_forward", True)
     _opt(b"tensor_core_pingpong", 2)      # bit mask: forward kernels | dH1 kernel; default: dH1 only
+    _opt(b"tensor_core_onchip", True)
 
 
 def _store(rng, cap, N, T, D, coop):
@@ -67,6 +68,7 @@ def test_tc_backward_matches_ffma_and_oracle(mixer, N, D, T, B, sharing):
     idx = rng.integers(0, 300, size=B).astype(np.int32)
     batch = lr.batch_from_store(s, idx)
     check_margin(lr, st, batch, hp)   # near-tie in the double-Q argmax: re-drawn by the decorator
+    st0 = lr.DqnState(st.theta.clone(), st.theta_tgt.clone(), st.agent_net, D, A)   # dqn_update steps st in place
     want = lr.dqn_update(st, batch, hp)
     ts = TrajStore(300, N, T, D, m.device)
     for k in ("obs", "act", "rew", "done", "filled"):
@@ -75,16 +77,18 @@ def test_tc_backward_matches_ffma_and_oracle(mixer, N, D, T, B, sharing):
     n = m.n_params
     scale = max(1.0, float(np.abs(want["grad"].numpy()).max()))
     grads = {}
-    for tc in (0, 2, 3, 1):   # 0: fused FP32 kernel; tensor-core pipeline -- 2: one tile at a time, 3: two accumulators everywhere, 1: the default (two accumulators in the dH1 kernel; applied below)
+    # 0: fused FP32 kernel; tensor-core passes -- 2 / 3: activations streamed through global memory (tc_train.cu), one tile at a time / two accumulators
+    # everywhere; 1: the default (tc_train3.cu: activations stay on chip; applied below)
+    for tc in (0, 2, 3, 1):
         _opt(b"tensor_core_backward", int(tc > 0))
+        _opt(b"tensor_core_onchip", int(tc == 1))
         _opt(b"tensor_core_pingpong", {0: 0, 2: 0, 3: 3, 1: 2}[tc])
         m.update_grads(ts, idx_d)
         torch.cuda.synchronize()
         g = m.grad.cpu().numpy()
         grads[tc] = g[:n] / g[n + 1]
         assert abs(g[n] / g[n + 1] - want["loss"]) <= 1e-5 * max(1.0, abs(want["loss"])), (tc, g[n] / g[n + 1], want["loss"])
-        err = np.abs(grads[tc] - want["grad"].numpy()).max() / scale
-        assert err < 1e-5, (tc, err)
+        assert_grad_close(lr, st0, batch, hp, grads[tc], want["grad"].numpy(), what=f"kernel selection {tc}:")
     assert all(np.abs(grads[0] - grads[k]).max() / scale < 1e-5 for k in (1, 2, 3))
     met = m.update_apply().cpu().numpy()  # applies the tensor-core gradients
     d = np.abs(m.theta.cpu().numpy() - st.theta.numpy())

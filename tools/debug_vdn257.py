@@ -17,8 +17,8 @@ def opt(name, v):
     nat.check(nat.lib().marl_set_option(name, C.c_int32(int(v))), "opt")
 
 
-def run(mixer, sharing, B, n_agents, attempt, bwd, pp):
-    opt(b"tensor_core_backward", bwd); opt(b"tensor_core_pingpong", pp)
+def run(mixer, sharing, B, n_agents, attempt, bwd, pp, onchip=1):
+    opt(b"tensor_core_backward", bwd); opt(b"tensor_core_pingpong", pp); opt(b"tensor_core_onchip", onchip)
     torch.manual_seed(1000 * attempt + B)
     rng = np.random.default_rng(B)
     hp = lr.DqnHP(mixer=mixer, target_update_interval_or_tau=2)
@@ -56,7 +56,7 @@ def run(mixer, sharing, B, n_agents, attempt, bwd, pp):
         scale = max(1.0, float(np.abs(want["grad"].numpy()).max()))
         err = np.abs(gr[:n] / gr[n + 1] - want["grad"].numpy()) / scale
         w = int(err.argmax())
-        print(f"bwd={bwd} pp={pp} attempt={attempt} u={u} margin={margin:.2e} |dq|max={dq:.2e} argmax flips on filled rows={flips} grad err max={err.max():.2e} at {w} (P={n // 2}) "
+        print(f"bwd={bwd} pp={pp} onchip={onchip} mixer={mixer} B={B} attempt={attempt} u={u} margin={margin:.2e} |dq|max={dq:.2e} argmax flips on filled rows={flips} grad err max={err.max():.2e} at {w} (P={n // 2}) "
               f"n>1e-6: {(err > 1e-6).sum()} loss {gr[n] / gr[n + 1]:.8f} vs {want['loss']:.8f}", flush=True)
         m.update_apply()
         m.theta.copy_(st.theta); m.theta_tgt.copy_(st.theta_tgt); m.adam_m.copy_(st.m); m.adam_v.copy_(st.v)
@@ -64,6 +64,7 @@ def run(mixer, sharing, B, n_agents, attempt, bwd, pp):
 
 
 if __name__ == "__main__":
-    for bwd, pp in ((0, 0), (1, 0), (1, 2), (1, 3)):
-        for attempt in (0, 1):
-            run(1, False, 257, 2, attempt, bwd, pp)
+    for bwd, pp, oc in ((0, 0, 0), (1, 2, 0), (1, 2, 1)):
+        run(1, False, 257, 2, 0, bwd, pp, oc)
+        run(0, False, 1024, 2, 0, bwd, pp, oc)
+        run(0, [0, 1, 0], 33, 3, 0, bwd, pp, oc)
