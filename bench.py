@@ -40,7 +40,9 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the idqn workload: ncu --set full, one kernel at a time with ncu's cache flush in
 # front (cold L2; profiles/r1_tc_pipeline.md).  The warm, pipelined figure of the whole update is in profiles/r2_dram_traffic.md.
-TRAFFIC_NCU = {"tc_dqn_fwd_kernel": 9303552, "tc_dh1_kernel": 3705344, "tc_dw_kernel": 92672512}
+TRAFFIC_NCU = {"tc_dqn_fwd_kernel": 9303552, "tc_dh1_kernel": 3705344, "tc_dw_kernel": 92672512,
+               # on-chip pass (round 2): dram__bytes of one launch inside the running pipeline (ncu --cache-control none, profiles/r2_dram_traffic.md)
+               "tc_dqn_fwd3_kernel": 4300000, "tc_dh1w1_kernel": 10300000, "tc_dw2_kernel": 10300000}
 
 
 def parse():
@@ -60,6 +62,7 @@ def parse():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gradient exchange inside the fused reduce + Adam kernel over NVLink peer memory (default), or one NCCL all-reduce per update")
     ap.add_argument("--tc-backward", type=int, default=1, help="1 = tcgen05 training pipeline (default), 0 = fused FP32 FFMA training kernel")
+    ap.add_argument("--tc-onchip", type=int, default=1, help="1 = training pass with H1 / H2 / dH1 kept on chip (tc_train3.cu, default), 0 = streamed through global memory (tc_train.cu)")
     a = ap.parse_args()
     wl = WORKLOADS[a.config]
     a.envs = a.envs or wl["envs"]
@@ -315,6 +318,7 @@ def run_dqn_family(args, wl):
     coll = Collector(env, model, T)
     lib = nat.lib()
     nat.check(lib.marl_set_option(b"tensor_core_backward", C.c_int32(int(args.tc_backward))), "marl_set_option")
+    nat.check(lib.marl_set_option(b"tensor_core_onchip", C.c_int32(int(args.tc_onchip))), "marl_set_option")
     state = dict(pos=0, updates=0)
     steps_dev = H.steps_dev
     # pinned host mirrors for the e2e leg
@@ -433,19 +437,29 @@ def run_dqn_family(args, wl):
     tensor_peak = peaks.get("bf16_tflops_sustained", 1443.2)   # sustained figure: the kernel is timed inside a long step
     per_update_us = 1e3 * (ms / args.steps) / U   # upper bound: includes the rollout's share of the iteration
     if kernel_n:
-        # tensor-core training pass (DESIGN.md section 6): three kernels; the roofline object describes the slowest one
-        names = ["tc_dqn_fwd_kernel", "tc_dh1_kernel", "tc_dw_kernel"]
-        flops = [rows * FWD,                                                       # online forward
-                 rows * 2 * HIDDEN * HIDDEN,                                       # dH1 = dH2 x W2
-                 rows * 2 * (HIDDEN * HIDDEN + HIDDEN * obs_dim + n_act * HIDDEN + HIDDEN + HIDDEN + n_act)]   # dW2, dW1, dW3 and the bias sums
-        # algorithmic HBM bytes per update: H1, H2 written + read, dH1 written + read (FP32), 64-byte row records written + read twice,
-        # gathered observations, target outputs, per-CTA gradient partials
-        inter = [rows * (2 * 512 + 64) + rows * obs_dim * 4 + rows * n_act * 4, rows * (512 + 64), rows * (3 * 512 + 64 + obs_dim * 4) + n_sm * 4 * (model.n_params // model.n_nets)]
+        # tensor-core training pass (DESIGN.md section 4.3): three kernels; the roofline object describes the slowest one
+        P_net = model.n_params // model.n_nets
+        if args.tc_onchip:
+            names = ["tc_dqn_fwd3_kernel", "tc_dh1w1_kernel", "tc_dw2_kernel"]
+            flops = [rows * FWD + rows * 2 * (n_act * HIDDEN + n_act),                  # online forward, dW3 | db3
+                     rows * 2 * HIDDEN * HIDDEN + rows * 2 * HIDDEN * (obs_dim + 1),     # dH1 = dH2 x W2, dW1 | db1
+                     rows * 2 * HIDDEN * (HIDDEN + 1)]                                   # dW2 | db2 (the recomputed layer 1, rows * 2 * obs * 128, is overhead and not counted)
+            # algorithmic HBM bytes: what crosses the kernels is the gathered observation row (stored 32 floats wide) and the 64-byte row record
+            inter = [rows * (obs_dim * 4 + n_act * 4) + rows * (128 + 64) + n_sm * 4 * (n_act * HIDDEN + n_act),
+                     rows * (128 + 64) + n_sm * 4 * HIDDEN * (obs_dim + 1), rows * (128 + 64) + n_sm * 4 * HIDDEN * (HIDDEN + 1)]
+        else:
+            names = ["tc_dqn_fwd_kernel", "tc_dh1_kernel", "tc_dw_kernel"]
+            flops = [rows * FWD,                                                       # online forward
+                     rows * 2 * HIDDEN * HIDDEN,                                       # dH1 = dH2 x W2
+                     rows * 2 * (HIDDEN * HIDDEN + HIDDEN * obs_dim + n_act * HIDDEN + HIDDEN + HIDDEN + n_act)]   # dW2, dW1, dW3 and the bias sums
+            # algorithmic HBM bytes per update: H1, H2 written + read, dH1 written + read (FP32), 64-byte row records written + read twice,
+            # gathered observations, target outputs, per-CTA gradient partials
+            inter = [rows * (2 * 512 + 64) + rows * obs_dim * 4 + rows * n_act * 4, rows * (512 + 64), rows * (3 * 512 + 64 + obs_dim * 4) + n_sm * 4 * P_net]
         us = [1e3 * m / kernel_n for m in kernel_ms]
         k = max(range(3), key=lambda i: us[i])
         achieved = flops[k] / (us[k] * 1e-6) / 1e12
         roofline = {"bound": "tensor", "kernel": names[k], "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                    "traffic": TRAFFIC_NCU.get(names[k]) if args.config == "idqn" else None,   # dram bytes of one launch, ncu --set full, cold L2
+                    "traffic": TRAFFIC_NCU.get(names[k]) if args.config == "idqn" else None,   # dram bytes of one launch (ncu)
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; TF32 runs at half of it and 3xTF32 needs three MMAs per "
                                    "FP32-accurate product: the FP32-equivalent ceiling of this arithmetic is peak / 6)",
                     "fp32_equivalent_peak": tensor_peak / 6, "frac_of_fp32_equivalent_peak": achieved / (tensor_peak / 6),

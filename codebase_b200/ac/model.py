@@ -121,6 +121,7 @@ class A2CNetwork:
         return dist.sample().T.unsqueeze(-1).contiguous(), actor_hiddens
 
     def update_from_store(self, batch: TrajStore, n_envs: int, step: int):
+        """One `model.update(batch, step)` on the device batch (ac/train.py:176)."""
         nat.check(self._lib.marl_a2c_update(self._h, batch.ref(), C.c_int32(n_envs), C.c_int64(int(step)), nat.ptr(self._metrics), nat.stream_ptr()), "marl_a2c_update")
         return self._metrics
 
@@ -181,3 +182,22 @@ class A2CNetwork:
             self.close()
         except Exception:
             pass
+
+
+class PPONetwork(A2CNetwork):
+    """Independent PPO -- drop-in for marlbase/ac/model.py PPONetwork (249-352; `_target_: ac.model.PPONetwork`, configs/algorithm/ippo.yaml).
+    Same networks, rollout and n-step returns as A2CNetwork; `update` re-uses one batch for `num_epochs` optimisation steps with the clipped
+    surrogate (marl_ppo_update: collecting-policy log-probabilities once, then per epoch critic pass -> actor pass -> clip + Adam on the device,
+    target critic after the last epoch).  Metrics are the epochs' means, as the reference returns them."""
+
+    def __init__(self, obs_space, action_space, cfg, actor, critic, device, max_envs=None, max_episode_length=None):
+        super().__init__(obs_space, action_space, cfg, actor, critic, device, max_envs=max_envs, max_episode_length=max_episode_length)
+        self.num_epochs, self.ppo_clip = int(cfg.num_epochs), float(cfg.ppo_clip)
+
+    def update_from_store(self, batch: TrajStore, n_envs: int, step: int):
+        nat.check(self._lib.marl_ppo_update(self._h, batch.ref(), C.c_int32(n_envs), C.c_int64(int(step)), C.c_int32(self.num_epochs), C.c_float(self.ppo_clip),
+                                            nat.ptr(self._metrics), nat.stream_ptr()), "marl_ppo_update")
+        return self._metrics
+
+    def update_grads(self, batch, n_envs):
+        raise NotImplementedError("PPO's epochs each need their own optimiser step: the grads / apply split of the data-parallel A2C path does not apply")

@@ -37,6 +37,31 @@ __global__ void nstep_returns_kernel(NStepParams p) {
   p.ret[i] = acc;
 }
 
+// log-probabilities of the taken actions under the collecting policy (ac/model.py:281-292), from the actor outputs of every gathered row:
+// old_logp[a][b][t] = log_softmax(logits[a][b][t][:])[act[a][b][t]] -- the formulas of head_a2c_actor (learner_kernels.cu)
+struct OldLogpParams { const float* logits; TrajView traj; const int32_t* idx; int N, P, A; float* out; };
+__global__ void old_logp_kernel(OldLogpParams p) {
+  const int T = p.traj.T, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N * p.P * T) return;
+  const int a = i / (p.P * T), rem = i - a * p.P * T, b = rem / T, t = rem - b * T;
+  const float* q = p.logits + (((size_t)a * p.P + b) * (T + 1) + t) * p.A;
+  const int act = p.traj.act[((size_t)p.idx[b] * p.N + a) * T + t];
+  float m = q[0];
+  for (int o = 1; o < p.A; ++o) m = fmaxf(m, q[o]);
+  float s = 0.f;
+  for (int o = 0; o < p.A; ++o) s += expf(q[o] - m);
+  p.out[i] = q[act] - (m + logf(s));
+}
+
+// mean over the epochs of the six device metrics (ac/model.py:352)
+__global__ void mean_metrics_kernel(const float* per_epoch, int n_epochs, float* out) {
+  const int k = threadIdx.x;
+  if (k >= 6) return;
+  float s = 0.f;
+  for (int e = 0; e < n_epochs; ++e) s += per_epoch[6 * e + k];
+  out[k] = k == 4 ? per_epoch[4] : s / (float)n_epochs;   // [4] = filled count (the same every epoch)
+}
+
 __global__ void iota_kernel(int32_t* x, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = i;
@@ -57,7 +82,9 @@ struct marl_a2c {
   int32_t* idx = nullptr;
   uint8_t* image = nullptr;  // packed weight images for the tensor-core forward path
   int64_t opt_steps = 0;
+  float *logits_all = nullptr, *old_logp = nullptr, *epoch_metrics = nullptr;   // PPO (allocated on first use)
 };
+constexpr int kMaxPpoEpochs = 64;
 
 extern "C" {
 
@@ -66,6 +93,7 @@ int marl_a2c_destroy(marl_a2c* h) {
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch); cudaFree(h->loss_part);
   cudaFree(h->vt); cudaFree(h->ret); cudaFree(h->adv); cudaFree(h->metrics); cudaFree(h->idx); cudaFree(h->image);
+  cudaFree(h->logits_all); cudaFree(h->old_logp); cudaFree(h->epoch_metrics);
   delete h;
   return MARL_OK;
 }
@@ -145,47 +173,61 @@ int marl_a2c_forward_critic(marl_a2c* h, const float* obs, int32_t n_envs, int32
   return a2c_dense_forward(h, h->critic, use_target ? h->theta_tgt : h->theta + h->n_actor, obs, n_envs, values_out, stream);
 }
 
-int marl_a2c_update_grads(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs, void* stream) {
-  MARL_REQUIRE(h && batch, "marl_a2c_update_grads: NULL argument");
-  MARL_REQUIRE(n_envs >= 1 && n_envs <= h->max_envs && n_envs <= batch->capacity, "marl_a2c_update_grads: n_envs %d out of range", n_envs);
-  MARL_REQUIRE(batch->T >= 1 && batch->T <= h->max_T, "marl_a2c_update_grads: T %d exceeds max_T %d", batch->T, h->max_T);
-  MARL_REQUIRE(batch->n_agents == h->actor.n_agents && batch->obs_dim == h->actor.in, "marl_a2c_update_grads: batch shape mismatch");
+struct A2cPass { RowSource src; RowPlan cplan, aplan; };
+
+// target-critic pass + n-step returns (ac/model.py:190-201): everything of an update that does not depend on the trainable parameters
+static int a2c_prepare(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs, cudaStream_t st, A2cPass& ps) {
+  MARL_REQUIRE(h && batch, "marl_a2c_update: NULL argument");
+  MARL_REQUIRE(n_envs >= 1 && n_envs <= h->max_envs && n_envs <= batch->capacity, "marl_a2c_update: n_envs %d out of range", n_envs);
+  MARL_REQUIRE(batch->T >= 1 && batch->T <= h->max_T, "marl_a2c_update: T %d exceeds max_T %d", batch->T, h->max_T);
+  MARL_REQUIRE(batch->n_agents == h->actor.n_agents && batch->obs_dim == h->actor.in, "marl_a2c_update: batch shape mismatch");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
   const int T = batch->T, N = h->actor.n_agents;
   const int min_units = (64 + T) / (T + 1) > 0 ? (64 + T) / (T + 1) : 1;
-  RowSource src; memset(&src, 0, sizeof(src));
-  src.mode = 1; src.traj = to_view(batch); src.idx = h->idx; src.N = N; src.D = h->actor.in;
-  const RowPlan cplan = make_plan(h->critic, n_envs, T + 1, h->n_sm, min_units);
-  const RowPlan aplan = make_plan(h->actor, n_envs, T + 1, h->n_sm, min_units);
+  memset(&ps.src, 0, sizeof(ps.src));
+  ps.src.mode = 1; ps.src.traj = to_view(batch); ps.src.idx = h->idx; ps.src.N = N; ps.src.D = h->actor.in;
+  ps.cplan = make_plan(h->critic, n_envs, T + 1, h->n_sm, min_units);
+  ps.aplan = make_plan(h->actor, n_envs, T + 1, h->n_sm, min_units);
   // 1. target critic on all T+1 observations (ac/model.py:190-193)
-  if (int rc = forward_any(h->critic, cplan, src, h->theta_tgt, h->image, h->vt, st)) return rc;
+  if (int rc = forward_any(h->critic, ps.cplan, ps.src, h->theta_tgt, h->image, h->vt, st)) return rc;
   // 2. n-step returns (ac/model.py:198-201)
-  NStepParams np; np.vt = h->vt; np.traj = src.traj; np.idx = h->idx; np.N = N; np.P = n_envs; np.n_steps = h->hp.n_steps; np.ret = h->ret;
+  NStepParams np; np.vt = h->vt; np.traj = ps.src.traj; np.idx = h->idx; np.N = N; np.P = n_envs; np.n_steps = h->hp.n_steps; np.ret = h->ret;
   for (int k = 0; k <= h->hp.n_steps; ++k) np.gpow[k] = (float)pow((double)h->hp.gamma, (double)k);
   nstep_returns_kernel<<<(N * n_envs * T + 255) / 256, 256, 0, st>>>(np);
   MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
+}
+
+// critic and actor training passes -> grad[] (un-normalised sums) + loss statistics; old_logp != NULL: PPO's clipped surrogate
+static int a2c_gradients(marl_a2c* h, const A2cPass& ps, cudaStream_t st, const float* old_logp, float ppo_clip) {
   // 3. critic: forward, value loss, backward; leaves advantage = returns - V for the actor pass
   TrainParams tp; memset(&tp, 0, sizeof(tp));
-  tp.plan = cplan; tp.src = src; tp.theta = h->theta + h->n_actor; tp.lay = h->critic.lay; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch;
+  tp.plan = ps.cplan; tp.src = ps.src; tp.theta = h->theta + h->n_actor; tp.lay = h->critic.lay; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch;
   tp.loss_part = h->loss_part; tp.returns = h->ret; tp.adv_out = h->adv; tp.value_coef = h->hp.value_loss_coef;
   if (int rc = launch_train(tp, kHeadA2cCritic, st)) return rc;
   ReduceParams rp; memset(&rp, 0, sizeof(rp));  // (sumsq_part stays NULL: two passes write different gradient slices)
   rp.scratch = h->scratch; rp.loss_part = h->loss_part; rp.n_nets = h->critic.n_nets; rp.P = h->critic.lay.P; rp.scratch_pitch = h->scratch_pitch;
-  memcpy(rp.cta_begin, cplan.cta_begin, sizeof(rp.cta_begin));
-  rp.n_loss_parts = cplan.cta_begin[cplan.n_nets]; rp.grad = h->grad + h->n_actor; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0;
+  memcpy(rp.cta_begin, ps.cplan.cta_begin, sizeof(rp.cta_begin));
+  rp.n_loss_parts = ps.cplan.cta_begin[ps.cplan.n_nets]; rp.grad = h->grad + h->n_actor; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0;
   if (int rc = launch_grad_reduce(rp, st)) return rc;
-  // 4. actor: forward, log-softmax, policy-gradient + entropy loss, backward
-  tp.plan = aplan; tp.theta = h->theta; tp.lay = h->actor.lay; tp.adv = h->adv; tp.entropy_coef = h->hp.entropy_coef;
+  // 4. actor: forward, log-softmax, policy-gradient (or clipped surrogate) + entropy loss, backward
+  tp.plan = ps.aplan; tp.theta = h->theta; tp.lay = h->actor.lay; tp.adv = h->adv; tp.entropy_coef = h->hp.entropy_coef;
+  tp.old_logp = old_logp; tp.ppo_clip = ppo_clip;
   if (int rc = launch_train(tp, kHeadA2cActor, st)) return rc;
-  rp.n_nets = h->actor.n_nets; rp.P = h->actor.lay.P; memcpy(rp.cta_begin, aplan.cta_begin, sizeof(rp.cta_begin));
-  rp.n_loss_parts = aplan.cta_begin[aplan.n_nets]; rp.grad = h->grad; rp.stats_accumulate = 1;
+  rp.n_nets = h->actor.n_nets; rp.P = h->actor.lay.P; memcpy(rp.cta_begin, ps.aplan.cta_begin, sizeof(rp.cta_begin));
+  rp.n_loss_parts = ps.aplan.cta_begin[ps.aplan.n_nets]; rp.grad = h->grad; rp.stats_accumulate = 1;
   return launch_grad_reduce(rp, st);
+}
+
+int marl_a2c_update_grads(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs, void* stream) {
+  A2cPass ps;
+  if (int rc = a2c_prepare(h, batch, n_envs, (cudaStream_t)stream, ps)) return rc;
+  return a2c_gradients(h, ps, (cudaStream_t)stream, nullptr, 0.f);
 }
 
 /* metrics_out device float[6] = (policy-gradient term, grad norm, entropy, value_loss, filled count, 0):
  * actor_loss = m[0] - entropy_coef*m[2]; loss = actor_loss + value_loss_coef*m[3]  (ac/model.py:216-226,241-246) */
-int marl_a2c_update_apply(marl_a2c* h, int64_t step, float* metrics_out, void* stream) {
+static int a2c_apply(marl_a2c* h, int64_t step, float* metrics_out, void* stream, bool target_update) {
   MARL_REQUIRE(h != nullptr, "marl_a2c_update_apply: NULL handle");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   h->opt_steps += 1;
@@ -197,10 +239,41 @@ int marl_a2c_update_apply(marl_a2c* h, int64_t step, float* metrics_out, void* s
   ap.bc2_sqrt = (float)sqrt(1.0 - pow((double)h->hp.beta2, (double)h->opt_steps));
   const float tu = h->hp.target_update_interval_or_tau;  // ac/model.py:233-239: `step` counts environment steps
   ap.tau = tu;
-  if (tu > 1.0f && fmod((double)step, (double)tu) == 0.0) ap.target_mode = 1;
-  else if (tu < 1.0f) ap.target_mode = 2;
+  if (target_update && tu > 1.0f && fmod((double)step, (double)tu) == 0.0) ap.target_mode = 1;
+  else if (target_update && tu < 1.0f) ap.target_mode = 2;
   ap.loss_out = metrics_out ? metrics_out : h->metrics;
   return launch_adam(ap, (cudaStream_t)stream);
+}
+
+int marl_a2c_update_apply(marl_a2c* h, int64_t step, float* metrics_out, void* stream) { return a2c_apply(h, step, metrics_out, stream, true); }
+
+/* PPONetwork.update (ac/model.py:265-352) on the same handle: returns and the collecting policy's log-probabilities once, then `num_epochs`
+ * optimisation steps on the same batch with the clipped surrogate (-min(r adv, clip(r, 1 -+ ppo_clip) adv) - entropy_coef H + value_loss_coef
+ * value loss; clip_grad_norm_ over all parameters when hp.grad_clip > 0), the target critic synchronised after the last epoch.
+ * metrics_out: device float[6] as marl_a2c_update, averaged over the epochs ([0] = the surrogate term). */
+int marl_ppo_update(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs, int64_t step, int32_t num_epochs, float ppo_clip, float* metrics_out, void* stream) {
+  MARL_REQUIRE(h != nullptr && num_epochs >= 1 && num_epochs <= kMaxPpoEpochs, "marl_ppo_update: num_epochs %d out of range (1..%d)", (int)num_epochs, kMaxPpoEpochs);
+  MARL_REQUIRE(ppo_clip > 0.f, "marl_ppo_update: ppo_clip must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  A2cPass ps;
+  if (int rc = a2c_prepare(h, batch, n_envs, st, ps)) return rc;
+  if (!h->logits_all) {
+    const size_t rows = (size_t)h->actor.n_agents * h->max_envs * (h->max_T + 1);
+    int rc = dev_alloc_zero(&h->logits_all, rows * h->actor.out) | dev_alloc_zero(&h->old_logp, rows) | dev_alloc_zero(&h->epoch_metrics, 6 * kMaxPpoEpochs);
+    if (rc) return MARL_ENOMEM;
+  }
+  // log-probabilities of the taken actions under the collecting policy = the current actor (ac/model.py:281-292)
+  if (int rc = forward_any(h->actor, ps.aplan, ps.src, h->theta, h->image, h->logits_all, st)) return rc;
+  OldLogpParams op; op.logits = h->logits_all; op.traj = ps.src.traj; op.idx = h->idx; op.N = h->actor.n_agents; op.P = n_envs; op.A = h->actor.out; op.out = h->old_logp;
+  old_logp_kernel<<<(op.N * n_envs * batch->T + 255) / 256, 256, 0, st>>>(op);
+  MARL_CUDA_TRY(cudaGetLastError());
+  for (int e = 0; e < num_epochs; ++e) {
+    if (int rc = a2c_gradients(h, ps, st, h->old_logp, ppo_clip)) return rc;
+    if (int rc = a2c_apply(h, step, h->epoch_metrics + 6 * e, stream, e == num_epochs - 1)) return rc;
+  }
+  mean_metrics_kernel<<<1, 32, 0, st>>>(h->epoch_metrics, num_epochs, metrics_out ? metrics_out : h->metrics);
+  MARL_CUDA_TRY(cudaGetLastError());
+  return MARL_OK;
 }
 
 int marl_a2c_update(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs, int64_t step, float* metrics_out, void* stream) {

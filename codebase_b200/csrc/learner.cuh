@@ -129,6 +129,10 @@ struct TrainParams {
   // kHeadA2cActor: parts = (sum -logp*adv*filled, 0, sum entropy*filled, 0)
   const float* adv;       // [N][B][T]
   float entropy_coef;
+  // PPO (ac/model.py:305-321): old_logp != NULL switches the actor head to the clipped surrogate -min(ratio adv, clip(ratio, 1 -+ ppo_clip) adv),
+  // ratio = exp(logp - old_logp); parts[0] = sum of that term * filled
+  const float* old_logp;  // [N][B][T] log-probabilities of the taken actions under the policy the batch was collected with
+  float ppo_clip;
 };
 
 struct ReduceParams {

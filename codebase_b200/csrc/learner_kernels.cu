@@ -268,11 +268,24 @@ __device__ __forceinline__ void head_a2c_actor(const TrainParams& p, const RowCt
     pr[o] = o < c.A ? expf(ls[o]) : 0.f;
     ent -= pr[o] * ls[o];
   }
-  st[0] += -ls[act] * adv * filled;                         // ac/model.py:216-219
+  float w = adv;   // dLoss/dlogp[act] = -w
+  if (p.old_logp != nullptr) {
+    // PPO clipped surrogate (ac/model.py:309-321).  torch.min sends the gradient to the smaller argument (half to each on a tie), clamp passes it
+    // inside [1 - c, 1 + c]: d(-min(r adv, clamp(r) adv))/dlogp = -adv r k, k = 1 when the unclipped term is the minimum or r is inside the range.
+    const float ratio = expf(ls[act] - p.old_logp[i]);
+    const float lo = 1.f - p.ppo_clip, hi = 1.f + p.ppo_clip;
+    const float surr1 = ratio * adv, surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
+    const float inrange = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+    const float k = surr1 < surr2 ? 1.f : (surr1 > surr2 ? inrange : 0.5f + 0.5f * inrange);
+    st[0] += -fminf(surr1, surr2) * filled;
+    w = adv * ratio * k;
+  } else {
+    st[0] += -ls[act] * adv * filled;                       // ac/model.py:216-219
+  }
   st[2] += ent * filled;
 #pragma unroll
   for (int o = 0; o < kOutPad; ++o)
-    dq[o] = o < c.A ? filled * (adv * (pr[o] - (o == act ? 1.f : 0.f)) + p.entropy_coef * pr[o] * (ls[o] + ent)) : 0.f;
+    dq[o] = o < c.A ? filled * (w * (pr[o] - (o == act ? 1.f : 0.f)) + p.entropy_coef * pr[o] * (ls[o] + ent)) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -260,6 +260,11 @@ int marl_a2c_update_grads(marl_a2c* a, const marl_traj_view* batch, int32_t n_en
 int marl_a2c_update_apply(marl_a2c* a, int64_t step, float* metrics_out, void* stream);
 int marl_a2c_update(marl_a2c* a, const marl_traj_view* batch, int32_t n_envs, int64_t step, float* metrics_out,
                     void* stream);
+/* PPONetwork.update (marlbase/ac/model.py:265-352; configs/algorithm/ippo.yaml: num_epochs 4, ppo_clip 0.2, grad_clip 0.5) on an A2C handle:
+ * n-step returns and the collecting policy's log-probabilities once, then num_epochs optimisation steps on the same batch with the clipped
+ * surrogate; the target critic follows after the last epoch.  metrics_out: device float[6] as marl_a2c_update, averaged over the epochs. */
+int marl_ppo_update(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs, int64_t step, int32_t num_epochs, float ppo_clip,
+                    float* metrics_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -351,6 +351,58 @@ def a2c_losses(actor, critic, target, st: A2CState, batch, hp: A2CHP):
     return actor_loss, value_loss, ent, returns
 
 
+def ppo_update(st: A2CState, batch, hp: A2CHP, step: int, num_epochs: int = 4, ppo_clip: float = 0.2):
+    """PPONetwork.update (ac/model.py:265-352): returns and the collecting policy's log-probabilities once, then num_epochs steps on the clipped
+    surrogate; target critic after the last epoch; the metrics are the epochs' means.  Returns also the first epoch's raw gradients."""
+    N, D = len(st.actor_net), st.in_dim
+    obs = list(torch.split(batch["obss"], D, dim=-1))
+    obs_t = [o[:-1] for o in obs]
+    acts, filled = batch["actions"], batch["filled"]
+    with torch.no_grad():
+        next_value = torch.cat(agents_forward(st.target, st.critic_net, obs, D, 1), dim=-1)
+        done = batch["dones"].float().unsqueeze(-1).repeat(1, 1, N)
+        returns = nstep_returns(batch["rewards"], done, next_value, hp.n_steps, hp.gamma)
+        old = [F.log_softmax(l, dim=-1) for l in agents_forward(st.actor, st.actor_net, obs_t, D, st.n_actions)]
+        old_logp = torch.cat([lp.gather(-1, acts[..., i:i + 1]) for i, lp in enumerate(old)], dim=-1)
+    out = dict(loss=[], actor_loss=[], value_loss=[], entropy=[])
+    first = None
+    for _ in range(num_epochs):
+        actor = st.actor.clone().requires_grad_(True)
+        critic = st.critic.clone().requires_grad_(True)
+        values = torch.cat(agents_forward(critic, st.critic_net, obs_t, D, 1), dim=-1)
+        logp_all = [F.log_softmax(l, dim=-1) for l in agents_forward(actor, st.actor_net, obs_t, D, st.n_actions)]
+        logp = torch.cat([lp.gather(-1, acts[..., i:i + 1]) for i, lp in enumerate(logp_all)], dim=-1)
+        entropy = torch.stack([-(lp.exp() * lp).sum(-1) for lp in logp_all], dim=-1).sum(-1)
+        adv = returns - values
+        value_loss = adv.pow(2).sum(-1)
+        ratio = torch.exp(logp - old_logp)
+        surr1, surr2 = ratio * adv.detach(), torch.clamp(ratio, 1.0 - ppo_clip, 1.0 + ppo_clip) * adv.detach()
+        actor_loss = -torch.min(surr1, surr2).sum(-1) - hp.entropy_coef * entropy
+        actor_loss = (actor_loss * filled).sum() / filled.sum()
+        value_loss = (value_loss * filled).sum() / filled.sum()
+        loss = actor_loss + hp.value_loss_coef * value_loss
+        g_actor, g_critic = torch.autograd.grad(loss, (actor, critic))
+        if first is None:
+            first = dict(actor=g_actor.clone(), critic=g_critic.clone())
+        if hp.grad_clip:
+            total = torch.linalg.vector_norm(torch.cat([g_actor, g_critic]))
+            coef = torch.clamp(hp.grad_clip / (total + 1e-6), max=1.0)
+            g_actor, g_critic = g_actor * coef, g_critic * coef
+        st.steps += 1
+        adam_step(st.actor, st.m["actor"], st.v["actor"], g_actor, st.steps, hp.lr)
+        adam_step(st.critic, st.m["critic"], st.v["critic"], g_critic, st.steps, hp.lr)
+        for k, v in (("loss", loss), ("actor_loss", actor_loss), ("value_loss", value_loss), ("entropy", (entropy * filled).sum() / filled.sum())):
+            out[k].append(float(v.detach()))
+    tu = hp.target_update_interval_or_tau
+    if tu > 1.0 and step % tu == 0:
+        st.target.copy_(st.critic)
+    elif tu < 1.0:
+        st.target.copy_((1 - tu) * st.target + tu * st.critic)
+    res = {k: sum(v) / len(v) for k, v in out.items()}
+    res.update(grad=first, returns=returns, per_epoch=out)
+    return res
+
+
 def a2c_update(st: A2CState, batch, hp: A2CHP, step: int):
     actor = st.actor.clone().requires_grad_(True)
     critic = st.critic.clone().requires_grad_(True)
