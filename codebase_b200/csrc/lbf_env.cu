@@ -24,11 +24,14 @@ struct LbfCfgDev {
   int R, C, N, NF, S, minp, maxp, minf, maxf, max_steps, time_limit, force_coop, normalize, coop_reward;
   double penalty;
   int RC, pitch, G, D;
+  int obs_id, std_rew;   // ObserveID / StandardiseReward wrappers (marlbase/utils/wrappers.py:75-103, 111-141)
 };
 
 struct LbfStateDev {
   int8_t* field; uint32_t* players; int32_t* step; int32_t* food_spawned; float* ep_return; int32_t* ep_len;
   uint32_t* episode_idx; uint8_t* active;
+  float* stdr;       // StandardiseReward state per env: wmean[N] | t[N] | sumw (float32 like the wrapper's numpy arrays); survives resets
+  int32_t* stdr_n;   // [E] number of rewards seen
 };
 
 struct TrajDev {
@@ -137,6 +140,10 @@ __device__ int list_foods(const LbfCfgDev& c, const int8_t* f, uint32_t* foods, 
 }
 
 __device__ void build_obs(const LbfCfgDev& c, const uint32_t* foods, int nf, const uint32_t* pl, int agent, float* out) {
+  if (c.obs_id) {  // ObserveID.observation (wrappers.py:96-103): np.eye(n_agents) concatenated in front
+    for (int j = 0; j < c.N; ++j) out[j] = j == agent ? 1.f : 0.f;
+    out += c.N;
+  }
   const int pr = (int)(pl[agent] & 0xFF), pc = (int)((pl[agent] >> 8) & 0xFF);
   const int r0 = imax(pr - c.S, 0), r1 = imin(pr + c.S + 1, c.R), c0 = imax(pc - c.S, 0), c1 = imin(pc + c.S + 1, c.C);
   int k = 0;
@@ -354,12 +361,35 @@ __global__ void __launch_bounds__(kThreads) lbf_step_kernel(LbfCfgDev c, LbfStat
   const bool trunc = active && (c.time_limit > 0 && step1 >= c.time_limit);
   const bool finished = done || trunc;
 
+  // StandardiseReward.reward (wrappers.py:119-141), the wrapper's numpy arithmetic: float32 state arrays, float64 where the python-float reward list
+  // enters (q, r, the standardised reward), float32 for the variance.  RecordEpisodeStatistics sits inside it and keeps the raw reward.
+  double rew_w = rew;
+  if (c.std_rew) {
+    float wmean = 0.f, tt = 0.f, sumw = 0.f; int n = 0;
+    float* st = s.stdr + (size_t)(env_ok ? e : 0) * (2 * c.N + 1);
+    if (alive) { wmean = st[sub]; tt = st[c.N + sub]; sumw = st[2 * c.N]; n = s.stdr_n[e]; }
+    __syncwarp();   // every agent lane has read sumw / n before lane 0 of the env writes them
+    if (alive) {
+      const double q = __dsub_rn(rew, (double)wmean);                                        // (no FMA contraction: numpy rounds every operation)
+      const float temp_sumw = __fadd_rn(sumw, 1.0f);
+      const double r = __ddiv_rn(q, (double)temp_sumw);
+      wmean = (float)__dadd_rn((double)wmean, r);
+      tt = (float)__dadd_rn((double)tt, __dmul_rn(__dmul_rn(q, r), (double)sumw));
+      n += 1;
+      st[sub] = wmean; st[c.N + sub] = tt;
+      if (sub == 0) { st[2 * c.N] = temp_sumw; s.stdr_n[e] = n; }
+      if (n > 1) {
+        const float var = __fdiv_rn(__fmul_rn(tt, (float)n), __fmul_rn(temp_sumw, (float)(n - 1)));
+        rew_w = __ddiv_rn(__dsub_rn(rew, (double)wmean), (double)__fadd_rn(__fsqrt_rn(var), 1e-6f));
+      }
+    }
+  }
   double tot = 0.0;  // CooperativeReward: python sum() over agents in index order
   for (int i = 0; i < c.N; ++i) {
-    const double ri = __shfl_sync(FULL, rew, gbase + i);
+    const double ri = __shfl_sync(FULL, rew_w, gbase + i);
     tot += ri;
   }
-  const float rew_f = (float)(c.coop_reward ? tot : rew);
+  const float rew_f = (float)(c.coop_reward ? tot : rew_w);
   float ep_ret = 0.f;
   if (alive) {
     ep_ret = s.ep_return[(size_t)e * c.N + sub] + (float)rew;  // float32 accumulation, raw reward (wrappers.py:33)
@@ -479,7 +509,8 @@ static LbfCfgDev to_dev(const marl_lbf_cfg& c) {
   d.penalty = c.penalty;
   d.RC = c.rows * c.cols; d.pitch = (d.RC + 15) & ~15;
   int g = 1; while (g < c.n_agents) g <<= 1;
-  d.G = g; d.D = 3 * c.max_num_food + 3 * c.n_agents;
+  d.obs_id = c.observe_id ? 1 : 0; d.std_rew = c.standardise_rewards ? 1 : 0;
+  d.G = g; d.D = 3 * c.max_num_food + 3 * c.n_agents + (d.obs_id ? c.n_agents : 0);
   return d;
 }
 
@@ -499,7 +530,7 @@ static int check_traj(const marl_lbf* env, const marl_traj_view* t) {
 
 extern "C" {
 
-int marl_lbf_obs_dim(const marl_lbf_cfg* cfg) { return cfg ? 3 * cfg->max_num_food + 3 * cfg->n_agents : MARL_EINVAL; }
+int marl_lbf_obs_dim(const marl_lbf_cfg* cfg) { return cfg ? 3 * cfg->max_num_food + 3 * cfg->n_agents + (cfg->observe_id ? cfg->n_agents : 0) : MARL_EINVAL; }
 
 int marl_lbf_create(const marl_lbf_cfg* cfg, int32_t n_envs, uint64_t seed, uint32_t env_gid0, int32_t device, marl_lbf** out) {
   MARL_REQUIRE(out != nullptr, "marl_lbf_create: out is NULL");
@@ -526,6 +557,8 @@ int marl_lbf_create(const marl_lbf_cfg* cfg, int32_t n_envs, uint64_t seed, uint
   ALLOC0(h->st.ep_len, E * 4);
   ALLOC0(h->st.episode_idx, E * 4);
   ALLOC0(h->st.active, E);
+  ALLOC0(h->st.stdr, E * (2 * d.N + 1) * 4);
+  ALLOC0(h->st.stdr_n, E * 4);
 #undef ALLOC0
   const int EPC = (kThreads / 32) * (32 / d.G);
   h->step_smem = (size_t)EPC * d.pitch + (size_t)EPC * d.G * 4 + (size_t)EPC * d.NF * 4 + (size_t)EPC * 16 + (size_t)EPC * d.N * d.D * 4;
@@ -544,7 +577,7 @@ int marl_lbf_destroy(marl_lbf* h) {
   if (!h) return MARL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->st.field); cudaFree(h->st.players); cudaFree(h->st.step); cudaFree(h->st.food_spawned);
-  cudaFree(h->st.ep_return); cudaFree(h->st.ep_len); cudaFree(h->st.episode_idx); cudaFree(h->st.active);
+  cudaFree(h->st.ep_return); cudaFree(h->st.ep_len); cudaFree(h->st.episode_idx); cudaFree(h->st.active); cudaFree(h->st.stdr); cudaFree(h->st.stdr_n);
   delete h;
   return MARL_OK;
 }

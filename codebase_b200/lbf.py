@@ -34,10 +34,12 @@ class LbfConfig:
     normalize_reward: int = 1
     cooperative_reward: int = 0
     penalty: float = 0.0
+    observe_id: int = 0            # env.observe_id: ObserveID wrapper (one-hot agent id in front of every observation)
+    standardise_rewards: int = 0   # env.standardise_rewards: StandardiseReward wrapper (per-env running statistics)
 
     @property
     def obs_dim(self) -> int:
-        return 3 * self.max_num_food + 3 * self.n_agents
+        return 3 * self.max_num_food + 3 * self.n_agents + (self.n_agents if self.observe_id else 0)
 
     @property
     def n_actions(self) -> int:

@@ -94,14 +94,13 @@ def make_env(seed, enable_video=False, name=None, time_limit=None, clear_info=Fa
     factory); the B200 overlays set it to thousands."""
     if enable_video:
         raise NotImplementedError("video recording is out of scope of the B200 hot path (algorithm.video_interval must stay False)")
-    if observe_id or standardise_rewards:
-        raise NotImplementedError("env.observe_id / env.standardise_rewards are not implemented on the B200 path yet")
     wrappers = list(wrappers or [])
     unknown = [w for w in wrappers if w not in SUPPORTED_WRAPPERS]
     if unknown:
         raise NotImplementedError(f"env.wrappers {unknown} are not implemented on the B200 path (supported: {sorted(SUPPORTED_WRAPPERS)})")
     cfg = parse_env_id(name, time_limit or 0, **kwargs)
     cfg.cooperative_reward = int("CooperativeReward" in wrappers)
+    cfg.observe_id, cfg.standardise_rewards = int(bool(observe_id)), int(bool(standardise_rewards))   # envs.py:97-101, inside the listed wrappers
     if seed is None:
         seed = random.randint(0, 99999)  # envs.py:58-59
     return B200VecEnv(cfg, int(parallel_envs or 1), int(seed), env_gid0, device)

@@ -64,6 +64,9 @@ typedef struct {
   int32_t normalize_reward;
   int32_t cooperative_reward;  /* CooperativeReward wrapper (configs/algorithm/vdn.yaml:6-8) */
   double  penalty;
+  int32_t observe_id;          /* ObserveID wrapper (marlbase/utils/wrappers.py:75-103, env.observe_id): one-hot agent id in front of every observation */
+  int32_t standardise_rewards; /* StandardiseReward wrapper (wrappers.py:111-141, env.standardise_rewards): per-env running mean / variance, applied
+                                  after RecordEpisodeStatistics (which keeps the raw rewards) and before CooperativeReward (envs.py:97-109) */
 } marl_lbf_cfg;
 
 typedef struct marl_lbf marl_lbf;
@@ -97,7 +100,7 @@ typedef struct {
 int marl_lbf_create(const marl_lbf_cfg* cfg, int32_t n_envs, uint64_t seed, uint32_t env_gid0, int32_t device,
                     marl_lbf** out);
 int marl_lbf_destroy(marl_lbf* env);
-int marl_lbf_obs_dim(const marl_lbf_cfg* cfg);             /* 3*max_num_food + 3*n_agents */
+int marl_lbf_obs_dim(const marl_lbf_cfg* cfg);             /* 3*max_num_food + 3*n_agents (+ n_agents with observe_id) */
 int marl_lbf_state_ptrs(marl_lbf* env, marl_lbf_state* out);
 /* Overwrite the transition state (parity tests): host or device pointers are NOT mixed -- all device. */
 int marl_lbf_set_state(marl_lbf* env, const int8_t* field /*[E][rows*cols] dense*/, const int8_t* players,

@@ -18,7 +18,7 @@ class OracleCfg(C.Structure):
         ("sight", C.c_int32), ("min_player_level", C.c_int32), ("max_player_level", C.c_int32),
         ("min_food_level", C.c_int32), ("max_food_level", C.c_int32), ("max_episode_steps", C.c_int32),
         ("time_limit", C.c_int32), ("force_coop", C.c_int32), ("normalize_reward", C.c_int32),
-        ("cooperative_reward", C.c_int32), ("penalty", C.c_double),
+        ("cooperative_reward", C.c_int32), ("penalty", C.c_double), ("observe_id", C.c_int32), ("standardise_rewards", C.c_int32),
     ]
 
 
@@ -26,6 +26,7 @@ class _State(C.Structure):
     _fields_ = [
         ("field", C.c_void_p), ("players", C.c_void_p), ("step", C.c_void_p), ("food_spawned", C.c_void_p),
         ("ep_return", C.c_void_p), ("ep_len", C.c_void_p), ("episode_idx", C.c_void_p), ("active", C.c_void_p),
+        ("stdr", C.c_void_p), ("stdr_n", C.c_void_p),
     ]
 
 
@@ -48,7 +49,7 @@ def lib():
 def make_cfg(**kw) -> OracleCfg:
     d = dict(rows=8, cols=8, n_agents=2, max_num_food=3, sight=8, min_player_level=1, max_player_level=2,
              min_food_level=1, max_food_level=0, max_episode_steps=50, time_limit=25, force_coop=0,
-             normalize_reward=1, cooperative_reward=0, penalty=0.0)
+             normalize_reward=1, cooperative_reward=0, penalty=0.0, observe_id=0, standardise_rewards=0)
     d.update(kw)
     return OracleCfg(**d)
 
@@ -71,7 +72,7 @@ class OracleVecEnv:
     def __init__(self, cfg: OracleCfg, n_envs: int, seed: int, env_gid0: int = 0):
         self.cfg, self.E, self.seed, self.gid0 = cfg, n_envs, seed, env_gid0
         N, RC = cfg.n_agents, cfg.rows * cfg.cols
-        self.N, self.D = N, 3 * cfg.max_num_food + 3 * N
+        self.N, self.D = N, 3 * cfg.max_num_food + 3 * N + (N if cfg.observe_id else 0)
         self.field = np.zeros((n_envs, RC), np.int8)
         self.players = np.zeros((n_envs, N, 4), np.int8)
         self.step_count = np.zeros(n_envs, np.int32)
@@ -80,8 +81,10 @@ class OracleVecEnv:
         self.ep_len = np.zeros(n_envs, np.int32)
         self.episode_idx = np.zeros(n_envs, np.uint32)
         self.active = np.zeros(n_envs, np.uint8)
+        self.stdr = np.zeros((n_envs, 2 * N + 1), np.float32)
+        self.stdr_n = np.zeros(n_envs, np.int32)
         self._st = _State(_p(self.field), _p(self.players), _p(self.step_count), _p(self.food_spawned),
-                          _p(self.ep_return), _p(self.ep_len), _p(self.episode_idx), _p(self.active))
+                          _p(self.ep_return), _p(self.ep_len), _p(self.episode_idx), _p(self.active), _p(self.stdr), _p(self.stdr_n))
 
     def reset(self, mask=None):
         obs = np.zeros((self.E, self.N, self.D), np.float32)

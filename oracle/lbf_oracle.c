@@ -59,7 +59,7 @@ static uint32_t ds_next(draw_stream* d) {
 /* integer in [lo, hi) -- multiply-shift, the same mapping the kernel uses */
 static int ds_randint(draw_stream* d, int lo, int hi) { return lo + (int)mulhi32(ds_next(d), (uint32_t)(hi - lo)); }
 
-int lbf_oracle_obs_dim(const lbf_oracle_cfg* c) { return 3 * c->max_num_food + 3 * c->n_agents; }
+int lbf_oracle_obs_dim(const lbf_oracle_cfg* c) { return 3 * c->max_num_food + 3 * c->n_agents + (c->observe_id ? c->n_agents : 0); }
 
 #define F(r_, c_) field[(r_) * C + (c_)]
 
@@ -203,6 +203,10 @@ void lbf_oracle_step_one(const lbf_oracle_cfg* cfg, int8_t* field, int8_t* playe
 }
 
 void lbf_oracle_obs_one(const lbf_oracle_cfg* cfg, const int8_t* field, const int8_t* players, int agent, float* out) {
+  if (cfg->observe_id) { /* ObserveID.observation (wrappers.py:96-103): np.eye(n_agents) concatenated in front */
+    for (int j = 0; j < cfg->n_agents; ++j) out[j] = j == agent ? 1.f : 0.f;
+    out += cfg->n_agents;
+  }
   const int R = cfg->rows, C = cfg->cols, N = cfg->n_agents, S = cfg->sight, NF = cfg->max_num_food;
   const int pr = players[4 * agent], pc = players[4 * agent + 1];
   const int r0 = pr - S < 0 ? 0 : pr - S, r1 = pr + S + 1 > R ? R : pr + S + 1;
@@ -268,6 +272,24 @@ void lbf_oracle_step(const lbf_oracle_cfg* c, int32_t n_envs, uint64_t seed, uin
     /* RecordEpisodeStatistics sits inside CooperativeReward (envs.py:97-109): it sees raw rewards, as float32 */
     for (int i = 0; i < N; ++i) s->ep_return[(size_t)e * N + i] += (float)raw[i];
     s->ep_len[e] += 1;
+    if (c->standardise_rewards) { /* StandardiseReward.reward (wrappers.py:119-141) with numpy's types: f32 state, f64 where the reward list enters */
+      float* st = s->stdr + (size_t)e * (2 * N + 1);
+      const float sumw = st[2 * N], temp_sumw = sumw + 1.0f;
+      const int n = s->stdr_n[e] + 1;
+      for (int i = 0; i < N; ++i) {
+        const double q = raw[i] - (double)st[i];
+        const double r = q / (double)temp_sumw;
+        st[i] = (float)((double)st[i] + r);
+        const double qr = q * r;
+        st[N + i] = (float)((double)st[N + i] + qr * (double)sumw);
+        if (n > 1) {
+          const float num = st[N + i] * (float)n, den = temp_sumw * (float)(n - 1);
+          const float var = num / den;
+          raw[i] = (raw[i] - (double)st[i]) / (double)(sqrtf(var) + 1e-6f);
+        }
+      }
+      st[2 * N] = temp_sumw; s->stdr_n[e] = n;
+    }
     double tot = 0.0;
     for (int i = 0; i < N; ++i) tot += raw[i];
     for (int i = 0; i < N; ++i) rew_out[(size_t)e * N + i] = (float)(c->cooperative_reward ? tot : raw[i]);

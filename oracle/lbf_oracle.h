@@ -37,6 +37,8 @@ typedef struct {
   int32_t normalize_reward;
   int32_t cooperative_reward;  /* CooperativeReward wrapper (wrappers.py:106-108, vdn.yaml:6-8) */
   double  penalty;
+  int32_t observe_id;          /* ObserveID (wrappers.py:75-103) */
+  int32_t standardise_rewards; /* StandardiseReward (wrappers.py:111-141), between RecordEpisodeStatistics and CooperativeReward (envs.py:97-109) */
 } lbf_oracle_cfg;
 
 /* Philox4x32-10 (Random123).  Pinned by the published known-answer vectors in tests/. */
@@ -64,6 +66,8 @@ typedef struct {
   int32_t*  ep_len;       /* [E] */
   uint32_t* episode_idx;  /* [E] number of resets so far */
   uint8_t*  active;       /* [E] */
+  float*    stdr;         /* [E][2N+1] StandardiseReward state: wmean[N] | t[N] | sumw (float32, like the wrapper's arrays); may be NULL without the flag */
+  int32_t*  stdr_n;       /* [E] */
 } lbf_oracle_state;
 
 void lbf_oracle_reset(const lbf_oracle_cfg* c, int32_t n_envs, uint64_t seed, uint32_t env_gid0,

@@ -69,10 +69,16 @@ class LBFConfig:
     normalize_reward: int = 1
     cooperative_reward: int = 0
     penalty: float = 0.0
+    observe_id: int = 0
+    standardise_rewards: int = 0
+
+    @property
+    def base_obs_dim(self):
+        return 3 * self.max_num_food + 3 * self.n_agents
 
     @property
     def obs_dim(self):
-        return 3 * self.max_num_food + 3 * self.n_agents
+        return self.base_obs_dim + (self.n_agents if self.observe_id else 0)
 
 
 class _Player:
@@ -223,7 +229,7 @@ class ForagingRef:
         s = c.sight
         r0, c0 = max(me.position[0] - s, 0), max(me.position[1] - s, 0)
         window = self.field[r0 : min(me.position[0] + s + 1, c.rows), c0 : min(me.position[1] + s + 1, c.cols)]
-        out = np.zeros(c.obs_dim, np.float32)
+        out = np.zeros(c.base_obs_dim, np.float32)
         out[: 3 * c.max_num_food] = np.tile(np.array([-1, -1, 0], np.float32), c.max_num_food)
         out[3 * c.max_num_food :] = np.tile(np.array([-1, -1, 0], np.float32), c.n_agents)
         for i, (y, x) in enumerate(zip(*np.nonzero(window))):
@@ -256,8 +262,9 @@ class ForagingRef:
 
 
 class WrappedForaging:
-    """ForagingRef under marlbase's wrapper stack: TimeLimit(time_limit) -> RecordEpisodeStatistics ->
-    [CooperativeReward]  (marlbase/utils/envs.py:93-109)."""
+    """ForagingRef under marlbase's wrapper stack: TimeLimit(time_limit) -> RecordEpisodeStatistics -> [ObserveID] -> [StandardiseReward] ->
+    [CooperativeReward]  (marlbase/utils/envs.py:93-109).  The two optional wrappers transcribe the reference's numpy code literally
+    (wrappers.py:96-103 and 119-141): they are what pins the C restatement and the kernel for these two flags."""
 
     def __init__(self, cfg: LBFConfig, seed: int, env_gid: int = 0):
         self.cfg, self.seed, self.gid = cfg, seed, env_gid
@@ -265,13 +272,42 @@ class WrappedForaging:
         self.n_resets = 0
         self.episode_reward = np.zeros(cfg.n_agents, np.float32)
         self.episode_length = 0
+        # StandardiseReward.__init__ (wrappers.py:112-117)
+        self.stdr_wrp_sumw = np.zeros(cfg.n_agents, dtype=np.float32)
+        self.stdr_wrp_wmean = np.zeros(cfg.n_agents, dtype=np.float32)
+        self.stdr_wrp_t = np.zeros(cfg.n_agents, dtype=np.float32)
+        self.stdr_wrp_n = 0
+
+    def _observation(self):
+        observation = tuple(self.env.obs(i) for i in range(self.cfg.n_agents))
+        if self.cfg.observe_id:   # ObserveID.observation (wrappers.py:96-103)
+            n_agents = self.cfg.n_agents
+            observation = np.stack(observation)
+            observation = np.concatenate((np.eye(n_agents, dtype=observation.dtype), observation), axis=1)
+            observation = tuple(o.squeeze() for o in np.split(observation, n_agents))
+        return observation
+
+    def _standardise(self, reward):
+        """StandardiseReward.reward (wrappers.py:119-141), verbatim arithmetic"""
+        weight = 1.0
+        q = reward - self.stdr_wrp_wmean
+        temp_sumw = self.stdr_wrp_sumw + weight
+        r = q * weight / temp_sumw
+        self.stdr_wrp_wmean += r
+        self.stdr_wrp_t += q * r * self.stdr_wrp_sumw
+        self.stdr_wrp_sumw = temp_sumw
+        self.stdr_wrp_n += 1
+        if self.stdr_wrp_n == 1:
+            return reward
+        var = (self.stdr_wrp_t * self.stdr_wrp_n) / (self.stdr_wrp_sumw * (self.stdr_wrp_n - 1))
+        return (reward - self.stdr_wrp_wmean) / (np.sqrt(var) + 1e-6)
 
     def reset(self):
         self.env.reset(self.seed, self.gid, self.n_resets)
         self.n_resets += 1
         self.episode_reward = np.zeros(self.cfg.n_agents, np.float32)
         self.episode_length = 0
-        return tuple(self.env.obs(i) for i in range(self.cfg.n_agents)), {}
+        return self._observation(), {}
 
     def step(self, actions):
         c = self.cfg
@@ -285,7 +321,8 @@ class WrappedForaging:
             for i, r in enumerate(self.episode_reward):
                 info[f"agent{i}/episode_returns"] = r
             info["episode_length"] = self.episode_length
+        if c.standardise_rewards:
+            reward = self._standardise(reward)
         if c.cooperative_reward:
             reward = c.n_agents * [sum(reward)]  # wrappers.py:106-108
-        obs = tuple(self.env.obs(i) for i in range(c.n_agents))
-        return obs, reward, done, truncated, info
+        return self._observation(), reward, done, truncated, info

@@ -64,10 +64,12 @@ CONFIGS = [
     dict(rows=15, cols=15, n_agents=4, max_num_food=5, sight=15, cooperative_reward=1),
     dict(rows=10, cols=10, n_agents=3, max_num_food=4, sight=2, penalty=0.1, force_coop=1),
     dict(rows=5, cols=5, n_agents=5, max_num_food=2, sight=5, normalize_reward=0),
+    dict(observe_id=1, standardise_rewards=1),                                                        # ObserveID + StandardiseReward (wrappers.py:75-141)
+    dict(rows=10, cols=10, n_agents=3, max_num_food=4, sight=2, penalty=0.1, standardise_rewards=1, cooperative_reward=1, observe_id=1),
 ]
 
 
-@pytest.mark.parametrize("cfgkw", CONFIGS, ids=["8x8-2p-3f", "15x15-4p-5f-coopreward", "10x10-3p-4f-2s-coop-pen", "5x5-5p-2f-raw"])
+@pytest.mark.parametrize("cfgkw", CONFIGS, ids=["8x8-2p-3f", "15x15-4p-5f-coopreward", "10x10-3p-4f-2s-coop-pen", "5x5-5p-2f-raw", "8x8-2p-3f-id-stdrew", "10x10-3p-4f-2s-pen-id-stdrew-coopreward"])
 def test_c_oracle_matches_python_restatement_on_random_rollouts(cfgkw):
     rng = np.random.default_rng(7)
     ccfg, pcfg, E = lbf_c.make_cfg(**cfgkw), lbf_ref.LBFConfig(**cfgkw), 24
