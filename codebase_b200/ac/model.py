@@ -25,8 +25,6 @@ class A2CNetwork:
                 raise NotImplementedError(f"{name}.layers={list(part.layers)}: the fused kernels implement the shipped [128, 128] MLP only")
         if critic.centralised:
             raise NotImplementedError("critic.centralised=True (MAA2C) is not implemented on the B200 path yet")
-        if getattr(cfg, "standardise_returns", False):
-            raise NotImplementedError("standardise_returns is not implemented on the B200 path")
         opt = getattr(cfg, "optimizer", "Adam")
         if (opt if isinstance(opt, str) else opt.__name__) != "Adam":
             raise NotImplementedError("only optimizer=Adam is implemented")
@@ -70,6 +68,17 @@ class A2CNetwork:
         self.theta[self.n_actor:].copy_(init_flat_params(self.n_critic_nets, self.in_dim, 1, critic.use_orthogonal_init))
         self.soft_update(1.0)
         self._metrics = torch.zeros(6, dtype=torch.float32, device=self.device)
+        self.standardise_returns = bool(getattr(cfg, "standardise_returns", False))   # ac/model.py:112-114
+        if self.standardise_returns:
+            nat.check(self._lib.marl_a2c_standardise_returns(self._h, C.c_int32(1)), "marl_a2c_standardise_returns")
+
+    def ret_ms(self):
+        """(mean[N], var[N], count) of the RunningMeanStd over the returns (standardise_returns), as CPU values."""
+        pm, pc = C.c_void_p(), C.c_void_p()
+        nat.check(self._lib.marl_a2c_ret_ms_ptrs(self._h, C.byref(pm), C.byref(pc)), "marl_a2c_ret_ms_ptrs")
+        ms = nat.device_view(pm.value, 2 * self.n_agents, self.device).cpu()
+        cnt = nat.device_view(pc.value, 1, self.device, "<f8").cpu()
+        return ms[: self.n_agents], ms[self.n_agents:], float(cnt[0])
 
     # ---- views into the flat parameter vector ------------------------------------------------------------------
     @property

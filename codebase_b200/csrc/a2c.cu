@@ -17,6 +17,7 @@ struct NStepParams {
   TrajView traj; const int32_t* idx; int N, P, n_steps;
   float gpow[kMaxNStep + 1];  // float32(gamma ** k), the Python-float powers of utils/utils.py:57-60
   float* ret;          // [N][P][T]
+  const float* ret_ms; // standardise_returns (ac/model.py:195-196): [mean[N] | var[N]] of the running return statistics, or NULL
 };
 
 // compute_nstep_returns (utils/utils.py:38-63): G_t = sum_{k<n} g^k r_{t+k}(1-d_{t+k}) + g^n V(o_{t+n})(1-d_{t+n}), cut (no
@@ -31,10 +32,63 @@ __global__ void nstep_returns_kernel(NStepParams p) {
     const int tt = t + k;
     if (tt >= T) break;
     const float d = (float)p.traj.done[ep * (T + 1) + tt];
-    const float src = (k == p.n_steps) ? p.vt[((size_t)a * p.P + b) * (T + 1) + tt] : p.traj.rew[(ep * p.N + a) * T + tt];
+    float src;
+    if (k == p.n_steps) {
+      src = p.vt[((size_t)a * p.P + b) * (T + 1) + tt];
+      if (p.ret_ms) src = __fadd_rn(__fmul_rn(src, sqrtf(p.ret_ms[p.N + a])), p.ret_ms[a]);   // next_value * sqrt(var) + mean
+    } else {
+      src = p.traj.rew[(ep * p.N + a) * T + tt];
+    }
     acc += (p.gpow[k] * src) * (1.f - d);
   }
   p.ret[i] = acc;
+}
+
+// standardise_returns (ac/model.py:202-204, utils/standardise_stream.py:6-43): RunningMeanStd over ALL T x P returns per agent (unmasked, as the
+// reference), parallel-variance update, then returns <- (returns - mean) / sqrt(var).  Batch moments are accumulated in FP64 in a fixed order
+// (per-block partials, then one block): the reference's float32 torch.mean / torch.var differ from them by rounding only.
+constexpr int kRetBlocks = 64;
+struct RetMsParams { float* ret; int N, P, T; double* part; float* ret_ms; double* count; };   // part: [kRetBlocks][N][2]
+__global__ void __launch_bounds__(256) ret_moments_kernel(RetMsParams p) {
+  __shared__ double sh[256][2];
+  const int n_per = p.P * p.T;
+  for (int a = 0; a < p.N; ++a) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_per; i += kRetBlocks * 256) { const double x = (double)p.ret[(size_t)a * n_per + i]; s1 += x; s2 += x * x; }
+    sh[threadIdx.x][0] = s1; sh[threadIdx.x][1] = s2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) { sh[threadIdx.x][0] += sh[threadIdx.x + s][0]; sh[threadIdx.x][1] += sh[threadIdx.x + s][1]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { p.part[((size_t)blockIdx.x * p.N + a) * 2] = sh[0][0]; p.part[((size_t)blockIdx.x * p.N + a) * 2 + 1] = sh[0][1]; }
+    __syncthreads();
+  }
+}
+// one thread per agent: batch mean / unbiased variance, RunningMeanStd.update_from_moments in the reference's float32 operation order
+__global__ void ret_ms_update_kernel(RetMsParams p) {
+  const int a = threadIdx.x;
+  if (a >= p.N) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < kRetBlocks; ++b) { s1 += p.part[((size_t)b * p.N + a) * 2]; s2 += p.part[((size_t)b * p.N + a) * 2 + 1]; }
+  const double n = (double)p.P * p.T;
+  const double bm = s1 / n, bv = n > 1.0 ? (s2 - n * bm * bm) / (n - 1.0) : 0.0;
+  const float batch_mean = (float)bm, batch_var = (float)bv, batch_count = (float)n;
+  const double count = *p.count;
+  const float mean = p.ret_ms[a], var = p.ret_ms[p.N + a], cnt = (float)count, tot = (float)(count + n);
+  const float delta = __fsub_rn(batch_mean, mean);
+  const float new_mean = __fadd_rn(mean, __fdiv_rn(__fmul_rn(delta, batch_count), tot));
+  const float m_a = __fmul_rn(var, cnt), m_b = __fmul_rn(batch_var, batch_count);
+  const float m_2 = __fadd_rn(__fadd_rn(m_a, m_b), __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(delta, delta), cnt), batch_count), tot));
+  p.ret_ms[a] = new_mean; p.ret_ms[p.N + a] = __fdiv_rn(m_2, tot);
+  __syncthreads();
+  if (a == 0) *p.count = count + n;
+}
+__global__ void ret_standardise_kernel(RetMsParams p) {
+  const int n_per = p.P * p.T, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N * n_per) return;
+  const int a = i / n_per;
+  p.ret[i] = __fdiv_rn(__fsub_rn(p.ret[i], p.ret_ms[a]), sqrtf(p.ret_ms[p.N + a]));
 }
 
 // log-probabilities of the taken actions under the collecting policy (ac/model.py:281-292), from the actor outputs of every gathered row:
@@ -83,6 +137,8 @@ struct marl_a2c {
   uint8_t* image = nullptr;  // packed weight images for the tensor-core forward path
   int64_t opt_steps = 0;
   float *logits_all = nullptr, *old_logp = nullptr, *epoch_metrics = nullptr;   // PPO (allocated on first use)
+  // standardise_returns: RunningMeanStd(shape=(n_agents,)) -- mean[N] | var[N] (float32), count (a Python float in the reference), partial sums
+  int standardise = 0; float* ret_ms = nullptr; double* ret_count = nullptr; double* ret_part = nullptr;
 };
 constexpr int kMaxPpoEpochs = 64;
 
@@ -93,7 +149,7 @@ int marl_a2c_destroy(marl_a2c* h) {
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch); cudaFree(h->loss_part);
   cudaFree(h->vt); cudaFree(h->ret); cudaFree(h->adv); cudaFree(h->metrics); cudaFree(h->idx); cudaFree(h->image);
-  cudaFree(h->logits_all); cudaFree(h->old_logp); cudaFree(h->epoch_metrics);
+  cudaFree(h->logits_all); cudaFree(h->old_logp); cudaFree(h->epoch_metrics); cudaFree(h->ret_ms); cudaFree(h->ret_count); cudaFree(h->ret_part);
   delete h;
   return MARL_OK;
 }
@@ -192,9 +248,42 @@ static int a2c_prepare(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs,
   if (int rc = forward_any(h->critic, ps.cplan, ps.src, h->theta_tgt, h->image, h->vt, st)) return rc;
   // 2. n-step returns (ac/model.py:198-201)
   NStepParams np; np.vt = h->vt; np.traj = ps.src.traj; np.idx = h->idx; np.N = N; np.P = n_envs; np.n_steps = h->hp.n_steps; np.ret = h->ret;
+  np.ret_ms = h->standardise ? h->ret_ms : nullptr;
   for (int k = 0; k <= h->hp.n_steps; ++k) np.gpow[k] = (float)pow((double)h->hp.gamma, (double)k);
   nstep_returns_kernel<<<(N * n_envs * T + 255) / 256, 256, 0, st>>>(np);
   MARL_CUDA_TRY(cudaGetLastError());
+  if (h->standardise) {  // ac/model.py:202-204
+    RetMsParams rp; rp.ret = h->ret; rp.N = N; rp.P = n_envs; rp.T = T; rp.part = h->ret_part; rp.ret_ms = h->ret_ms; rp.count = h->ret_count;
+    ret_moments_kernel<<<kRetBlocks, 256, 0, st>>>(rp);
+    ret_ms_update_kernel<<<1, 32, 0, st>>>(rp);
+    ret_standardise_kernel<<<(N * n_envs * T + 255) / 256, 256, 0, st>>>(rp);
+    MARL_CUDA_TRY(cudaGetLastError());
+  }
+  return MARL_OK;
+}
+
+/* cfg.standardise_returns (ac/model.py:112-114): switches the RunningMeanStd over the n-step returns on (mean 0, var 1, count 1e-4) or off. */
+int marl_a2c_standardise_returns(marl_a2c* h, int32_t enable) {
+  MARL_REQUIRE(h != nullptr, "marl_a2c_standardise_returns: NULL handle");
+  MARL_REQUIRE(h->actor.n_agents <= 32, "marl_a2c_standardise_returns: at most 32 agents");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  if (enable && !h->ret_ms) {
+    const int N = h->actor.n_agents;
+    std::vector<float> init(2 * N, 0.f);
+    for (int a = 0; a < N; ++a) init[N + a] = 1.f;
+    const double c0 = 1e-4;
+    MARL_CUDA_TRY(cudaMalloc(&h->ret_ms, 2 * N * sizeof(float))); MARL_CUDA_TRY(cudaMalloc(&h->ret_count, sizeof(double)));
+    MARL_CUDA_TRY(cudaMalloc(&h->ret_part, (size_t)kRetBlocks * N * 2 * sizeof(double)));
+    MARL_CUDA_TRY(cudaMemcpy(h->ret_ms, init.data(), 2 * N * sizeof(float), cudaMemcpyHostToDevice));
+    MARL_CUDA_TRY(cudaMemcpy(h->ret_count, &c0, sizeof(double), cudaMemcpyHostToDevice));
+  }
+  h->standardise = enable ? 1 : 0;
+  return MARL_OK;
+}
+/* the running statistics as device pointers: ret_ms float[2 n_agents] = mean | var, count double[1] (NULL before the first enable) */
+int marl_a2c_ret_ms_ptrs(marl_a2c* h, float** ret_ms, double** count) {
+  MARL_REQUIRE(h != nullptr, "marl_a2c_ret_ms_ptrs: NULL handle");
+  if (ret_ms) *ret_ms = h->ret_ms; if (count) *count = h->ret_count;
   return MARL_OK;
 }
 

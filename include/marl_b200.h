@@ -263,6 +263,11 @@ int marl_a2c_update_grads(marl_a2c* a, const marl_traj_view* batch, int32_t n_en
 int marl_a2c_update_apply(marl_a2c* a, int64_t step, float* metrics_out, void* stream);
 int marl_a2c_update(marl_a2c* a, const marl_traj_view* batch, int32_t n_envs, int64_t step, float* metrics_out,
                     void* stream);
+/* cfg.standardise_returns of the actor-critic learners (marlbase/ac/model.py:112-114,195-204,272-281; utils/standardise_stream.py:6-43): a
+ * RunningMeanStd(shape=(n_agents,)) over the n-step returns of every update -- the bootstrap values are de-standardised with the statistics so far,
+ * the statistics absorb the batch's returns (all T x P of them, unmasked), the returns are standardised.  enable != 0 initialises them on first use. */
+int marl_a2c_standardise_returns(marl_a2c* a, int32_t enable);
+int marl_a2c_ret_ms_ptrs(marl_a2c* a, float** ret_ms /* mean[N] | var[N] */, double** count);
 /* PPONetwork.update (marlbase/ac/model.py:265-352; configs/algorithm/ippo.yaml: num_epochs 4, ppo_clip 0.2, grad_clip 0.5) on an A2C handle:
  * n-step returns and the collecting policy's log-probabilities once, then num_epochs optimisation steps on the same batch with the clipped
  * surrogate; the target critic follows after the last epoch.  metrics_out: device float[6] as marl_a2c_update, averaged over the epochs. */

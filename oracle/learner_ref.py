@@ -298,6 +298,22 @@ def nstep_returns(rewards, done, next_values, nsteps, gamma):
     return out
 
 
+class RunningMeanStdRef:
+    """utils/standardise_stream.py:6-43 restated (float32 tensors, Python-float count)"""
+
+    def __init__(self, shape, epsilon=1e-4):
+        self.mean, self.var, self.count = torch.zeros(shape, dtype=torch.float32), torch.ones(shape, dtype=torch.float32), epsilon
+
+    def update(self, arr):
+        arr = arr.reshape(-1, arr.size(-1))
+        batch_mean, batch_var, batch_count = torch.mean(arr, dim=0), torch.var(arr, dim=0), arr.shape[0]
+        delta = batch_mean - self.mean
+        tot_count = self.count + batch_count
+        new_mean = self.mean + delta * batch_count / tot_count
+        m_2 = self.var * self.count + batch_var * batch_count + torch.square(delta) * self.count * batch_count / (self.count + batch_count)
+        self.mean, self.var, self.count = new_mean, m_2 / (self.count + batch_count), batch_count + self.count
+
+
 @dataclass
 class A2CHP:
     lr: float = 3e-4
@@ -321,6 +337,7 @@ class A2CState:
     m: dict = field(default_factory=dict)
     v: dict = field(default_factory=dict)
     steps: int = 0             # optimiser steps taken
+    ret_ms: object = None      # RunningMeanStdRef(shape=(n_agents,)) when cfg.standardise_returns (ac/model.py:112-114), else None
 
     def __post_init__(self):
         for k in ("actor", "critic"):
@@ -334,8 +351,13 @@ def a2c_losses(actor, critic, target, st: A2CState, batch, hp: A2CHP):
     obs = list(torch.split(batch["obss"], D, dim=-1))
     with torch.no_grad():
         next_value = torch.cat(agents_forward(target, st.critic_net, obs, D, 1), dim=-1)                  # (T+1,P,N)
+    if st.ret_ms is not None:                                                                             # ac/model.py:195-196
+        next_value = next_value * torch.sqrt(st.ret_ms.var) + st.ret_ms.mean
     done = batch["dones"].float().unsqueeze(-1).repeat(1, 1, N)
     returns = nstep_returns(batch["rewards"], done, next_value, hp.n_steps, hp.gamma)
+    if st.ret_ms is not None:                                                                             # ac/model.py:202-204
+        st.ret_ms.update(returns)
+        returns = (returns - st.ret_ms.mean) / torch.sqrt(st.ret_ms.var)
     obs_t = [o[:-1] for o in obs]
     values = torch.cat(agents_forward(critic, st.critic_net, obs_t, D, 1), dim=-1)                       # (T,P,N)
     logits = agents_forward(actor, st.actor_net, obs_t, D, st.n_actions)
@@ -360,8 +382,13 @@ def ppo_update(st: A2CState, batch, hp: A2CHP, step: int, num_epochs: int = 4, p
     acts, filled = batch["actions"], batch["filled"]
     with torch.no_grad():
         next_value = torch.cat(agents_forward(st.target, st.critic_net, obs, D, 1), dim=-1)
+        if st.ret_ms is not None:                                                                         # ac/model.py:272-273
+            next_value = next_value * torch.sqrt(st.ret_ms.var) + st.ret_ms.mean
         done = batch["dones"].float().unsqueeze(-1).repeat(1, 1, N)
         returns = nstep_returns(batch["rewards"], done, next_value, hp.n_steps, hp.gamma)
+        if st.ret_ms is not None:                                                                         # ac/model.py:279-281
+            st.ret_ms.update(returns)
+            returns = (returns - st.ret_ms.mean) / torch.sqrt(st.ret_ms.var)
         old = [F.log_softmax(l, dim=-1) for l in agents_forward(st.actor, st.actor_net, obs_t, D, st.n_actions)]
         old_logp = torch.cat([lp.gather(-1, acts[..., i:i + 1]) for i, lp in enumerate(old)], dim=-1)
     out = dict(loss=[], actor_loss=[], value_loss=[], entropy=[])

@@ -40,6 +40,36 @@ def _oracle_batch(s):
 
 
 @pytest.mark.refsrc
+@pytest.mark.parametrize("cls", ["A2CNetwork", "PPONetwork"])
+def test_oracle_standardise_returns_matches_live_reference(cls):
+    """cfg.standardise_returns=True: RunningMeanStd over the n-step returns (ac/model.py:195-204, 272-281) -- oracle vs the live classes"""
+    from collections import namedtuple
+
+    from oracle import ref_shim
+
+    ref = ref_shim.load()
+    torch.manual_seed(9)
+    cfg = ref_shim.a2c_cfg(standardise_returns=True, num_epochs=3, ppo_clip=0.2, target_update_interval_or_tau=2)
+    net = ref_shim.net_cfg()
+    model = getattr(ref.ac_model, cls)([ref_shim.Space(shape=(D,))] * N, [ref_shim.Space(n=A)] * N, cfg, net, net, "cpu")
+    sd = model.state_dict()
+    st = lr.A2CState(lr.flat_from_state_dict(sd, "actor.independent", N), lr.flat_from_state_dict(sd, "critic.independent", N),
+                     lr.flat_from_state_dict(sd, "target_critic.independent", N), [0, 1], [0, 1], D, A, ret_ms=lr.RunningMeanStdRef((N,)))
+    hp = lr.A2CHP(target_update_interval_or_tau=2)
+    Batch = namedtuple("Batch", ["obss", "actions", "rewards", "dones", "filled", "action_masks"])
+    rng = np.random.default_rng(3)
+    for step in (0, 2, 3):
+        b = _oracle_batch(_batch_arrays(rng, 10, N))
+        want = model.update(Batch(b["obss"], b["actions"], b["rewards"], b["dones"].bool(), b["filled"], None), step)
+        got = lr.ppo_update(st, b, hp, step, 3, 0.2) if cls == "PPONetwork" else lr.a2c_update(st, b, hp, step)
+        _close([got[k] for k in ("loss", "actor_loss", "value_loss", "entropy")], [want[k] for k in ("loss", "actor_loss", "value_loss", "entropy")])
+    _close(st.ret_ms.mean.numpy(), model.ret_ms.mean.numpy()); _close(st.ret_ms.var.numpy(), model.ret_ms.var.numpy())
+    assert abs(st.ret_ms.count - model.ret_ms.count) < 1e-9
+    d = np.abs(st.actor.numpy() - lr.flat_from_state_dict(model.state_dict(), "actor.independent", N).numpy())
+    assert np.quantile(d, 0.999) < 1e-5
+
+
+@pytest.mark.refsrc
 @pytest.mark.parametrize("sharing,clip", [(False, False), (True, 0.5)])
 def test_oracle_ppo_matches_live_reference(sharing, clip):
     """three PPO updates (4 epochs each) of the reference's PPONetwork vs oracle.learner_ref.ppo_update from the same weights and batches"""
@@ -82,14 +112,14 @@ def test_oracle_ppo_first_epoch_is_a2c_with_unit_ratio():
     _close(g_ppo["actor"].numpy(), g_a2c["actor"].numpy()); _close(g_ppo["critic"].numpy(), g_a2c["critic"].numpy())
 
 
-def _model(sharing, hp, P, n_agents, num_epochs, ppo_clip):
-    from codebase_b200.ac.model import PPONetwork
+def _model(sharing, hp, P, n_agents, num_epochs, ppo_clip, standardise=False, cls="PPONetwork"):
+    from codebase_b200.ac import model as M
 
     cfg = types.SimpleNamespace(optimizer="Adam", lr=hp.lr, gamma=hp.gamma, grad_clip=hp.grad_clip, n_steps=hp.n_steps, entropy_coef=hp.entropy_coef,
-                                value_loss_coef=hp.value_loss_coef, target_update_interval_or_tau=hp.target_update_interval_or_tau, standardise_returns=False,
+                                value_loss_coef=hp.value_loss_coef, target_update_interval_or_tau=hp.target_update_interval_or_tau, standardise_returns=standardise,
                                 num_epochs=num_epochs, ppo_clip=ppo_clip)
     net = types.SimpleNamespace(layers=[128, 128], parameter_sharing=sharing, use_rnn=False, use_orthogonal_init=True, centralised=False)
-    return PPONetwork([_space(shape=(D,))] * n_agents, [_space(n=A)] * n_agents, cfg, net, net, "cuda", max_envs=P, max_episode_length=T)
+    return getattr(M, cls)([_space(shape=(D,))] * n_agents, [_space(n=A)] * n_agents, cfg, net, net, "cuda", max_envs=P, max_episode_length=T)
 
 
 @pytest.mark.gpu
@@ -116,6 +146,37 @@ def test_ppo_update_matches_oracle(sharing, P, n_agents, clip, epochs, lr_):
         assert np.quantile(d, 0.999) < 1e-5 * max(1.0, lr_ / 3e-4) and d.max() < 2 * hp.lr * epochs * (u + 1) + 1e-6, (np.quantile(d, 0.999), d.max())
         assert np.quantile(np.abs(m.theta_tgt.cpu().numpy() - st.target.numpy()), 0.999) < 1e-5 * max(1.0, lr_ / 3e-4)
         # keep the two trajectories glued so that later updates compare like for like
+        m.theta.copy_(torch.cat([st.actor, st.critic])); m.theta_tgt.copy_(st.target)
+        m.adam_m.copy_(torch.cat([st.m["actor"], st.m["critic"]])); m.adam_v.copy_(torch.cat([st.v["actor"], st.v["critic"]]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls", ["A2CNetwork", "PPONetwork"])
+def test_standardise_returns_matches_oracle(cls):
+    """cfg.standardise_returns=True on the device (marl_a2c_standardise_returns): metrics, running statistics and parameters against the oracle"""
+    from codebase_b200.lbf import TrajStore
+
+    P, n_agents, epochs = 200, 2, 3
+    rng = np.random.default_rng(21)
+    hp = lr.A2CHP(target_update_interval_or_tau=2)
+    m = _model(False, hp, P, n_agents, epochs, 0.2, standardise=True, cls=cls)
+    st = lr.A2CState(m.theta[: m.n_actor].cpu().clone(), m.theta[m.n_actor:].cpu().clone(), m.theta_tgt.cpu().clone(), [0, 1], [0, 1], D, A,
+                     ret_ms=lr.RunningMeanStdRef((n_agents,)))
+    for u, step in enumerate((0, 2, 5)):
+        s = _batch_arrays(rng, P, n_agents)
+        s["rew"] *= 3.0   # returns away from the unit scale the statistics start at
+        want = lr.ppo_update(st, _oracle_batch(s), hp, step, epochs, 0.2) if cls == "PPONetwork" else lr.a2c_update(st, _oracle_batch(s), hp, step)
+        ts = TrajStore(P, n_agents, T, D, m.device)
+        for k in ("obs", "act", "rew", "done", "filled"):
+            getattr(ts, k).copy_(torch.as_tensor(s[k]))
+        met = m.metrics_dict(m.update_from_store(ts, P, step))
+        _close([met["loss"], met["actor_loss"], met["value_loss"], met["entropy"]], [want["loss"], want["actor_loss"], want["value_loss"], want["entropy"]], rtol=2e-5, atol=2e-5)
+        mean, var, count = m.ret_ms()
+        _close(mean.numpy(), st.ret_ms.mean.numpy()); _close(var.numpy(), st.ret_ms.var.numpy()); assert abs(count - st.ret_ms.count) < 1e-6
+        _, ret, _ = m.scratch(P, T)
+        _close(ret.permute(2, 1, 0).cpu().numpy(), want["returns"].numpy(), rtol=2e-5, atol=2e-5)
+        d = np.abs(m.theta.cpu().numpy() - np.concatenate([st.actor.numpy(), st.critic.numpy()]))
+        assert np.quantile(d, 0.999) < 1e-5, (u, np.quantile(d, 0.999))
         m.theta.copy_(torch.cat([st.actor, st.critic])); m.theta_tgt.copy_(st.target)
         m.adam_m.copy_(torch.cat([st.m["actor"], st.m["critic"]])); m.adam_v.copy_(torch.cat([st.v["actor"], st.v["critic"]]))
 
