@@ -5,6 +5,7 @@
 // policy-gradient + entropy + value losses, Adam, target sync), for independent or shared per-agent networks with a
 // decentralised critic (critic.centralised: False, configs/algorithm/ia2c.yaml:18).
 #include "learner.cuh"
+#include "retms.cuh"
 #include <math.h>
 #include <vector>
 
@@ -42,53 +43,6 @@ __global__ void nstep_returns_kernel(NStepParams p) {
     acc += (p.gpow[k] * src) * (1.f - d);
   }
   p.ret[i] = acc;
-}
-
-// standardise_returns (ac/model.py:202-204, utils/standardise_stream.py:6-43): RunningMeanStd over ALL T x P returns per agent (unmasked, as the
-// reference), parallel-variance update, then returns <- (returns - mean) / sqrt(var).  Batch moments are accumulated in FP64 in a fixed order
-// (per-block partials, then one block): the reference's float32 torch.mean / torch.var differ from them by rounding only.
-constexpr int kRetBlocks = 64;
-struct RetMsParams { float* ret; int N, P, T; double* part; float* ret_ms; double* count; };   // part: [kRetBlocks][N][2]
-__global__ void __launch_bounds__(256) ret_moments_kernel(RetMsParams p) {
-  __shared__ double sh[256][2];
-  const int n_per = p.P * p.T;
-  for (int a = 0; a < p.N; ++a) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_per; i += kRetBlocks * 256) { const double x = (double)p.ret[(size_t)a * n_per + i]; s1 += x; s2 += x * x; }
-    sh[threadIdx.x][0] = s1; sh[threadIdx.x][1] = s2;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if ((int)threadIdx.x < s) { sh[threadIdx.x][0] += sh[threadIdx.x + s][0]; sh[threadIdx.x][1] += sh[threadIdx.x + s][1]; }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) { p.part[((size_t)blockIdx.x * p.N + a) * 2] = sh[0][0]; p.part[((size_t)blockIdx.x * p.N + a) * 2 + 1] = sh[0][1]; }
-    __syncthreads();
-  }
-}
-// one thread per agent: batch mean / unbiased variance, RunningMeanStd.update_from_moments in the reference's float32 operation order
-__global__ void ret_ms_update_kernel(RetMsParams p) {
-  const int a = threadIdx.x;
-  if (a >= p.N) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < kRetBlocks; ++b) { s1 += p.part[((size_t)b * p.N + a) * 2]; s2 += p.part[((size_t)b * p.N + a) * 2 + 1]; }
-  const double n = (double)p.P * p.T;
-  const double bm = s1 / n, bv = n > 1.0 ? (s2 - n * bm * bm) / (n - 1.0) : 0.0;
-  const float batch_mean = (float)bm, batch_var = (float)bv, batch_count = (float)n;
-  const double count = *p.count;
-  const float mean = p.ret_ms[a], var = p.ret_ms[p.N + a], cnt = (float)count, tot = (float)(count + n);
-  const float delta = __fsub_rn(batch_mean, mean);
-  const float new_mean = __fadd_rn(mean, __fdiv_rn(__fmul_rn(delta, batch_count), tot));
-  const float m_a = __fmul_rn(var, cnt), m_b = __fmul_rn(batch_var, batch_count);
-  const float m_2 = __fadd_rn(__fadd_rn(m_a, m_b), __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(delta, delta), cnt), batch_count), tot));
-  p.ret_ms[a] = new_mean; p.ret_ms[p.N + a] = __fdiv_rn(m_2, tot);
-  __syncthreads();
-  if (a == 0) *p.count = count + n;
-}
-__global__ void ret_standardise_kernel(RetMsParams p) {
-  const int n_per = p.P * p.T, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.N * n_per) return;
-  const int a = i / n_per;
-  p.ret[i] = __fdiv_rn(__fsub_rn(p.ret[i], p.ret_ms[a]), sqrtf(p.ret_ms[p.N + a]));
 }
 
 // log-probabilities of the taken actions under the collecting policy (ac/model.py:281-292), from the actor outputs of every gathered row:
@@ -254,10 +208,7 @@ static int a2c_prepare(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs,
   MARL_CUDA_TRY(cudaGetLastError());
   if (h->standardise) {  // ac/model.py:202-204
     RetMsParams rp; rp.ret = h->ret; rp.N = N; rp.P = n_envs; rp.T = T; rp.part = h->ret_part; rp.ret_ms = h->ret_ms; rp.count = h->ret_count;
-    ret_moments_kernel<<<kRetBlocks, 256, 0, st>>>(rp);
-    ret_ms_update_kernel<<<1, 32, 0, st>>>(rp);
-    ret_standardise_kernel<<<(N * n_envs * T + 255) / 256, 256, 0, st>>>(rp);
-    MARL_CUDA_TRY(cudaGetLastError());
+    MARL_CUDA_TRY(ret_ms_step(rp, st));
   }
   return MARL_OK;
 }

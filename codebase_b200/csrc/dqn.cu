@@ -4,6 +4,7 @@
 // update (zero_grad/backward/clip/Adam), update_target/hard_update/soft_update -- and ReplayBuffer.sample's index
 // draw + gather (marlbase/dqn/train.py:94-124).
 #include "learner.cuh"
+#include "retms.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -65,6 +66,67 @@ __global__ void __launch_bounds__(256) vdn_td_kernel(VdnTdParams p) {
   if (threadIdx.x == 0) { p.loss_part[4 * blockIdx.x] = red[0]; p.loss_part[4 * blockIdx.x + 1] = red[256]; p.loss_part[4 * blockIdx.x + 2] = 0.f; p.loss_part[4 * blockIdx.x + 3] = 0.f; }
 }
 
+// ---- cfg.standardise_returns (dqn/model.py:147-158, VDN 256-264): the TD target needs statistics of the whole batch's returns before any loss ----
+// 1. returns[c][b][t] = r + gamma * (target_qs * sqrt(var) + mean) * (1 - done[t + 1]) and chosen[c][b][t] = Q(o_t)[a_t] (VDN: both summed over the
+//    agents, c = 0); every (b, t), filled or not, as the reference.  Columns of the statistics: one per agent (IDQN); the reference's VDN reshapes
+//    its (E, B) returns with reshape(-1, B), i.e. one column per batch entry -- stat_per_b selects that.
+// 2. RunningMeanStd step (retms.cuh): statistics absorb the returns, returns are standardised in place.
+// 3. td[c][b][t] = 2 (chosen - returns) filled  +  the loss statistics.
+struct StdRetParams {
+  const float* q; const float* tq;  // [N][B][T+1][A]
+  TrajView traj; const int32_t* idx; int B, N, A, vdn; float gamma; int double_q;
+  const float* ret_ms; int n_stat, stat_per_b;   // mean[n_stat] | var[n_stat]
+  float* ret; float* chosen; float* td;          // [C][B][T], C = vdn ? 1 : N
+  float* loss_part;
+};
+__global__ void __launch_bounds__(256) std_returns_kernel(StdRetParams p) {
+  const int T = p.traj.T, C = p.vdn ? 1 : p.N, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= C * p.B * T) return;
+  const int c = i / (p.B * T), rem = i - c * p.B * T, b = rem / T, t = rem - b * T;
+  const size_t ep = (size_t)p.idx[b];
+  float chosen = 0.f, tsel = 0.f;
+  for (int a = (p.vdn ? 0 : c); a < (p.vdn ? p.N : c + 1); ++a) {
+    const size_t row = ((size_t)a * p.B + b) * (T + 1) + t;
+    const float* q0 = p.q + row * p.A; const float* q1 = q0 + p.A; const float* t1 = p.tq + (row + 1) * p.A;
+    chosen += q0[p.traj.act[(ep * p.N + a) * T + t]];
+    if (p.double_q) {
+      int best = 0; float bv = q1[0];
+      for (int o = 1; o < p.A; ++o) if (q1[o] > bv) { bv = q1[o]; best = o; }
+      tsel += t1[best];
+    } else {
+      float m = t1[0];
+      for (int o = 1; o < p.A; ++o) m = fmaxf(m, t1[o]);
+      tsel += m;
+    }
+  }
+  const int col = p.stat_per_b ? b : c;
+  tsel = __fadd_rn(__fmul_rn(tsel, sqrtf(p.ret_ms[p.n_stat + col])), p.ret_ms[col]);     // target_qs * sqrt(var) + mean
+  const float rew = p.traj.rew[(ep * p.N + (p.vdn ? 0 : c)) * T + t];
+  const float y = __fadd_rn(rew, __fmul_rn(__fmul_rn(p.gamma, tsel), 1.f - (float)p.traj.done[ep * (T + 1) + t + 1]));
+  // the statistics' columns must be contiguous: [col][...]
+  const size_t o = p.stat_per_b ? ((size_t)b * T + t) : (size_t)i;
+  p.ret[o] = y; p.chosen[o] = chosen;
+}
+__global__ void __launch_bounds__(256) std_td_kernel(StdRetParams p) {
+  __shared__ float red[512];
+  const int T = p.traj.T, C = p.vdn ? 1 : p.N, i = blockIdx.x * 256 + threadIdx.x;
+  float loss = 0.f, fill = 0.f;
+  if (i < C * p.B * T) {
+    const int c = i / (p.B * T), rem = i - c * p.B * T, b = rem / T, t = rem - b * T;
+    const float filled = (float)p.traj.filled[(size_t)p.idx[b] * T + t];
+    const float delta = p.chosen[i] - p.ret[i];
+    loss = delta * delta * filled; fill = c == 0 ? filled : 0.f;
+    p.td[i] = 2.f * delta * filled;
+  }
+  red[threadIdx.x] = loss; red[256 + threadIdx.x] = fill;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { red[threadIdx.x] += red[threadIdx.x + s]; red[256 + threadIdx.x] += red[256 + threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { p.loss_part[4 * blockIdx.x] = red[0]; p.loss_part[4 * blockIdx.x + 1] = red[256]; p.loss_part[4 * blockIdx.x + 2] = 0.f; p.loss_part[4 * blockIdx.x + 3] = 0.f; }
+}
+
 }  // namespace marl
 
 using namespace marl;
@@ -94,6 +156,8 @@ struct marl_dqn {
   // optional CUDA-event timing of the training kernel (bench.py's roofline leg)
   // measurement hook: 4 events per timed update (before the training pass, after each of its kernels; the FP32 path uses 0 and 3)
   bool timing = false; std::vector<cudaEvent_t> ev; int ev_used = 0; bool ev_split = false;
+  // cfg.standardise_returns: RunningMeanStd over the TD targets (mean[n] | var[n], count, partial sums, returns / chosen-Q scratch)
+  int standardise = 0, n_stat = 0; float *ret_ms = nullptr, *ret = nullptr, *chosen = nullptr; double *ret_count = nullptr, *ret_part = nullptr;
 };
 static const int kTimingPairs = 1024;
 
@@ -148,9 +212,42 @@ int marl_dqn_destroy(marl_dqn* h) {
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
   cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec); cudaFree(h->tc_x); cudaFree(h->grid_barrier);
   for (int r = 0; r < kMaxRanks; ++r) if (h->peer_base[r] != nullptr && r != h->xchg.rank) cudaIpcCloseMemHandle(h->peer_base[r]);
-  cudaFree(h->xbuf);
+  cudaFree(h->xbuf); cudaFree(h->ret_ms); cudaFree(h->ret); cudaFree(h->chosen); cudaFree(h->ret_count); cudaFree(h->ret_part);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
+  return MARL_OK;
+}
+
+/* cfg.standardise_returns (dqn/model.py:82-84, 221-222): RunningMeanStd over the TD targets, one column per agent (VDN: per batch entry, see the
+ * kernels above); mean 0, var 1, count 1e-4 on first enable. */
+int marl_dqn_standardise_returns(marl_dqn* h, int32_t enable) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_standardise_returns: NULL handle");
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  if (enable && !h->ret_ms) {
+    const int n = h->hp.mixer == 1 ? h->max_batch : h->ns.n_agents, C = h->hp.mixer == 1 ? 1 : h->ns.n_agents;
+    const size_t rows = (size_t)h->ns.n_agents * h->max_batch * (h->max_T + 1);
+    std::vector<float> init(2 * n, 0.f);
+    for (int a = 0; a < n; ++a) init[n + a] = 1.f;
+    const double c0 = 1e-4;
+    int rc = 0;
+    rc |= dqn_alloc(&h->ret_ms, 2 * n); rc |= dqn_alloc(&h->ret, (size_t)C * h->max_batch * h->max_T); rc |= dqn_alloc(&h->chosen, (size_t)C * h->max_batch * h->max_T);
+    if (!h->q_all) rc |= dqn_alloc(&h->q_all, rows * h->ns.out);
+    if (!h->td || h->hp.mixer == 0) { cudaFree(h->td); h->td = nullptr; rc |= dqn_alloc(&h->td, (size_t)C * h->max_batch * h->max_T); }
+    if (rc) return MARL_ENOMEM;
+    MARL_CUDA_TRY(cudaMalloc(&h->ret_count, sizeof(double))); MARL_CUDA_TRY(cudaMalloc(&h->ret_part, (size_t)kRetBlocks * n * 2 * sizeof(double)));
+    MARL_CUDA_TRY(cudaMemcpy(h->ret_ms, init.data(), 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    MARL_CUDA_TRY(cudaMemcpy(h->ret_count, &c0, sizeof(double), cudaMemcpyHostToDevice));
+    h->n_stat = n;
+    // the per-update loss statistics of this path come from one block per 256 (c, b, t) entries
+    cudaFree(h->loss_part); h->loss_part = nullptr;
+    if (dqn_alloc(&h->loss_part, 4 * ((size_t)h->n_sm + (size_t)C * h->max_batch * h->max_T / 256 + 2))) return MARL_ENOMEM;
+  }
+  h->standardise = enable ? 1 : 0;
+  return MARL_OK;
+}
+int marl_dqn_ret_ms_ptrs(marl_dqn* h, float** ret_ms, double** count, int32_t* n_stat) {
+  MARL_REQUIRE(h != nullptr, "marl_dqn_ret_ms_ptrs: NULL handle");
+  if (ret_ms) *ret_ms = h->ret_ms; if (count) *count = h->ret_count; if (n_stat) *n_stat = h->n_stat;
   return MARL_OK;
 }
 
@@ -207,7 +304,30 @@ static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* epi
   int n_loss_parts = plan.cta_begin[plan.n_nets];
   const float* td_ext = nullptr;
   float* loss_part = h->loss_part;
-  if (h->hp.mixer == 1) {  // VDN: online Q-values of all agents first, then the agent-summed TD error
+  int td_agent_stride = 0;
+  if (h->standardise) {
+    // online Q-values of every row, returns + chosen Q, RunningMeanStd step, TD error (dqn/model.py:147-158 / 256-264)
+    MARL_REQUIRE(h->hp.mixer == 0 || batch == h->n_stat, "marl_dqn_update: VDN's standardise_returns keeps one statistic per batch entry (the reference's reshape(-1, B)): "
+                 "batch %d must stay at max_batch %d", batch, h->n_stat);
+    if (int rc = forward_any(h->ns, plan, src, h->theta, h->image, h->q_all, st, h->image_current)) return rc;
+    h->image_current = tc_forward_enabled() != 0;
+    const int C = h->hp.mixer == 1 ? 1 : h->ns.n_agents;
+    StdRetParams sp; memset(&sp, 0, sizeof(sp));
+    sp.q = h->q_all; sp.tq = h->tq; sp.traj = src.traj; sp.idx = episode_idx; sp.B = batch; sp.N = h->ns.n_agents; sp.A = h->ns.out; sp.vdn = h->hp.mixer == 1;
+    sp.gamma = h->hp.gamma; sp.double_q = h->hp.double_q; sp.ret_ms = h->ret_ms; sp.n_stat = h->n_stat; sp.stat_per_b = h->hp.mixer == 1;
+    sp.ret = h->ret; sp.chosen = h->chosen; sp.td = h->td;
+    const int vb = (C * batch * T + 255) / 256;
+    sp.loss_part = h->loss_part + 4 * (size_t)n_loss_parts;
+    std_returns_kernel<<<vb, 256, 0, st>>>(sp);
+    RetMsParams rp; rp.ret = h->ret; rp.part = h->ret_part; rp.ret_ms = h->ret_ms; rp.count = h->ret_count; rp.T = T;
+    if (h->hp.mixer == 1) { rp.N = batch; rp.P = 1; } else { rp.N = C; rp.P = batch; }
+    MARL_CUDA_TRY(ret_ms_step(rp, st));
+    std_td_kernel<<<vb, 256, 0, st>>>(sp);
+    MARL_CUDA_TRY(cudaGetLastError());
+    n_loss_parts += vb;
+    td_ext = h->td;
+    td_agent_stride = h->hp.mixer == 1 ? 0 : batch * T;
+  } else if (h->hp.mixer == 1) {  // VDN: online Q-values of all agents first, then the agent-summed TD error
     if (int rc = forward_any(h->ns, plan, src, h->theta, h->image, h->q_all, st, h->image_current)) return rc;
     h->image_current = tc_forward_enabled() != 0;
     VdnTdParams vp; vp.q = h->q_all; vp.tq = h->tq; vp.traj = src.traj; vp.idx = episode_idx; vp.B = batch; vp.N = h->ns.n_agents; vp.A = h->ns.out;
@@ -220,7 +340,7 @@ static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* epi
     td_ext = h->td;
   }
   TrainParams tp; memset(&tp, 0, sizeof(tp));
-  tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext;
+  tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext; tp.td_agent_stride = td_agent_stride;
   tp.gamma = h->hp.gamma; tp.double_q = h->hp.double_q; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch; tp.loss_part = loss_part;
   const bool rec = h->timing && h->ev_used < kTimingPairs;
   if (rec) cudaEventRecord(h->ev[4 * h->ev_used], st);

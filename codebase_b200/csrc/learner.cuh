@@ -120,7 +120,8 @@ struct TrainParams {
   float* loss_part;       // [gridDim][4] per-CTA loss statistics, meaning depends on the head (see below)
   // kHeadDqn: parts = (sum delta^2*filled, sum filled on agent 0, 0, 0)
   const float* tq;        // target-net Q-values of every gathered row, [N][B][T+1][out] (from the forward kernel)
-  const float* td_ext;    // VDN: precomputed 2*delta*filled per (b, t), [B][T]; NULL for independent learners
+  const float* td_ext;    // precomputed 2*delta*filled (VDN: per (b, t), [B][T]; standardise_returns: per (agent, b, t) with td_agent_stride = B*T); NULL: the head computes it
+  int td_agent_stride;
   float gamma; int double_q;
   // kHeadA2cCritic: parts = (0, sum filled on agent 0, 0, sum adv^2*filled); writes adv = returns - V
   const float* returns;   // [N][B][T] n-step returns

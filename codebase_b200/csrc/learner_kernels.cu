@@ -218,7 +218,7 @@ __device__ __forceinline__ void head_dqn(const TrainParams& p, const RowCtx& c, 
   const float filled = c.filled;
   float g;
   if (p.td_ext) {  // VDN: the agent-coupled TD error was computed by vdn_td_kernel
-    g = p.td_ext[(size_t)c.b * c.T + c.tt];
+    g = p.td_ext[(size_t)c.agent * p.td_agent_stride + (size_t)c.b * c.T + c.tt];
   } else {
     const float rew = c.rew, done1 = c.done1;
     const float* tq = p.tq + (((size_t)c.agent * c.B + c.b) * (c.T + 1) + c.tt + 1) * c.A;

@@ -261,7 +261,7 @@ struct TcTrainParams {
   float* rec;                 // [rows][kRowRec] row records
   float* xg;                  // [rows][kMaxObsDim] gathered observation rows (zero padded to the staged width): the weight-gradient
                               // kernel reads them without chasing the episode index again
-  const float* tq; const float* td_ext; float gamma; int double_q;
+  const float* tq; const float* td_ext; int td_agent_stride; float gamma; int double_q;
   float* scratch; int scratch_pitch; float* loss_part;
   unsigned long long* dbg;    // profiling builds: host-mapped progress marks (NULL otherwise)
 };

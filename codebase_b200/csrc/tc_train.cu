@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd_kernel(TcTrainParams
         if (p.q_out) for (int o = 0; o < A; ++o) p.q_out[dst_row * A + o] = q[o];
         if (tt < T) {
           if (p.td_ext) {
-            g = p.td_ext[(size_t)b * T + tt];
+            g = p.td_ext[(size_t)agent * p.td_agent_stride + (size_t)b * T + tt];
           } else {
             const float* qn = (r + 1 < nrows) ? (qs + (r + 1) * kOutPad) : carry;
             const float* tq = p.tq + (((size_t)agent * B + b) * (T + 1) + tt + 1) * A;
@@ -738,7 +738,7 @@ int launch_tc_dqn_train(const TrainParams& tp, const TcBuffers& buf, cudaStream_
   TcTrainParams p; memset(&p, 0, sizeof(p));
   p.plan = tp.plan; p.src = tp.src; p.lay = tp.lay; p.images = buf.image; p.bwd_images = buf.bwd_image; p.q_out = nullptr;
   p.h1g = buf.h1; p.h2g = buf.h2; p.dh1g = buf.dh1; p.rec = buf.rec; p.xg = buf.x; p.rows = buf.rows;
-  p.tq = tp.tq; p.td_ext = tp.td_ext; p.gamma = tp.gamma; p.double_q = tp.double_q;
+  p.tq = tp.tq; p.td_ext = tp.td_ext; p.td_agent_stride = tp.td_agent_stride; p.gamma = tp.gamma; p.double_q = tp.double_q;
   p.scratch = tp.scratch; p.scratch_pitch = tp.scratch_pitch; p.loss_part = tp.loss_part;
   const int grid = tp.plan.cta_begin[tp.plan.n_nets];
   p.dbg = tc_debug_progress_ptr();

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) tc_dqn_fwd2_kernel(TcTrainParam
             const uint32_t act = (uint32_t)tv.act[(ep * tv.N + agent) * T + tt];
             mt[m].rew = tv.rew[(ep * tv.N + agent) * T + tt];
             fl = (act & 0xFFu) | ((uint32_t)tv.filled[ep * T + tt] << 8) | ((uint32_t)tv.done[ep * (T + 1) + tt + 1] << 9) | (1u << 10);
-            if (p.td_ext) mt[m].td = p.td_ext[(size_t)b * T + tt];
+            if (p.td_ext) mt[m].td = p.td_ext[(size_t)agent * p.td_agent_stride + (size_t)b * T + tt];
           }
           if (agent == 0) fl |= 1u << 11;
           mt[m].act_flags = fl;

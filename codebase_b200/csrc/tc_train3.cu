@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd3_kernel(TcTrainParam
         if (p.q_out) for (int o = 0; o < A; ++o) p.q_out[dst_row * A + o] = q[o];
         if (tt < T) {
           if (p.td_ext) {
-            g = p.td_ext[(size_t)b * T + tt];
+            g = p.td_ext[(size_t)agent * p.td_agent_stride + (size_t)b * T + tt];
           } else {
             const float* qn = (r + 1 < nrows) ? (qs + (r + 1) * kOutPad) : carry;
             const float* tq = p.tq + (((size_t)agent * B + b) * (T + 1) + tt + 1) * A;

@@ -83,8 +83,6 @@ class QNetwork:
             raise NotImplementedError("use_rnn=True (GRU) is out of scope of the B200 hot path (every shipped config has use_rnn: False)")
         if list(layers) != [HIDDEN, HIDDEN]:
             raise NotImplementedError(f"layers={list(layers)}: the fused kernels implement the shipped [128, 128] MLP only")
-        if getattr(cfg, "standardise_returns", False):
-            raise NotImplementedError("standardise_returns is not implemented on the B200 path (default False in every shipped config)")
         opt = getattr(cfg, "optimizer", "Adam")
         if (opt if isinstance(opt, str) else opt.__name__) != "Adam":
             raise NotImplementedError("only optimizer=Adam is implemented")
@@ -123,6 +121,16 @@ class QNetwork:
         self.hard_update()
         self._metrics = torch.zeros(6, dtype=torch.float32, device=self.device)
         self._idx = torch.zeros(self.max_batch, dtype=torch.int32, device=self.device)
+        self.standardise_returns = bool(getattr(cfg, "standardise_returns", False))   # dqn/model.py:82-84 (VDN: 221-222)
+        if self.standardise_returns:
+            nat.check(self._lib.marl_dqn_standardise_returns(self._h, C.c_int32(1)), "marl_dqn_standardise_returns")
+
+    def ret_ms(self):
+        """(mean, var, count) of the RunningMeanStd over the TD targets (standardise_returns): one entry per agent; VDN: per batch entry."""
+        pm, pc, n = C.c_void_p(), C.c_void_p(), C.c_int32()
+        nat.check(self._lib.marl_dqn_ret_ms_ptrs(self._h, C.byref(pm), C.byref(pc), C.byref(n)), "marl_dqn_ret_ms_ptrs")
+        ms = nat.device_view(pm.value, 2 * n.value, self.device).cpu()
+        return ms[: n.value], ms[n.value:], float(nat.device_view(pc.value, 1, self.device, "<f8").cpu()[0])
 
     # ---- reference API ------------------------------------------------------------------------------------------
     def init_hiddens(self, batch_size):

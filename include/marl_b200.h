@@ -181,6 +181,11 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
 int marl_dqn_destroy(marl_dqn* q);
 /* Device pointers to the flat parameter / optimiser state ([n_nets*P] floats each; grad has 4 extra floats:
  * loss numerator, filled count, 2 spare).  Initialise theta through these (orthogonal init is done by the caller). */
+/* cfg.standardise_returns of the DQN family (marlbase/dqn/model.py:82-84,147-158; VDN 221-222,256-264; utils/standardise_stream.py): a
+ * RunningMeanStd over the TD targets of every update -- target Q-values are de-standardised with the statistics so far, the statistics absorb the
+ * batch's returns, the returns are standardised before the loss.  One column per agent; VDN: one per batch entry (the reference's reshape). */
+int marl_dqn_standardise_returns(marl_dqn* q, int32_t enable);
+int marl_dqn_ret_ms_ptrs(marl_dqn* q, float** ret_ms /* mean[n] | var[n] */, double** count, int32_t* n_stat);
 int marl_dqn_param_ptrs(marl_dqn* q, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad,
                         int64_t* n_params);
 int marl_dqn_sync_target(marl_dqn* q, void* stream);        /* hard_update (dqn/model.py:195-196) */

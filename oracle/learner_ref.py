@@ -132,6 +132,7 @@ class DqnState:
     v: torch.Tensor = None
     updates: int = 0
     last_target_update: int = 0
+    ret_ms: object = None   # RunningMeanStdRef when cfg.standardise_returns (dqn/model.py:82-84: shape (n_agents,); VDN 221-222: shape (1,))
 
     def __post_init__(self):
         if self.m is None:
@@ -140,7 +141,7 @@ class DqnState:
             self.v = torch.zeros_like(self.theta)
 
 
-def dqn_loss(theta, theta_tgt, agent_net, in_dim, out_dim, batch, hp: DqnHP):
+def dqn_loss(theta, theta_tgt, agent_net, in_dim, out_dim, batch, hp: DqnHP, ret_ms=None):
     """batch = dict(obss (N,T+1,B,D) f32, actions (N,T,B) i64, rewards (N,T,B), dones (T+1,B) f32, filled (T,B) f32)"""
     obss, actions, rewards, dones, filled = (batch[k] for k in ("obss", "actions", "rewards", "dones", "filled"))
     N = obss.shape[0]
@@ -155,10 +156,22 @@ def dqn_loss(theta, theta_tgt, agent_net, in_dim, out_dim, batch, hp: DqnHP):
             target = tq.max(-1)[0]
     if hp.mixer == 1:
         chosen = chosen.sum(0)
-        returns = rewards[0] + hp.gamma * target.sum(0) * (1 - dones[1:])
+        target = target.sum(0)
+        if ret_ms is not None:                                           # dqn/model.py:256-257
+            target = target * torch.sqrt(ret_ms.var) + ret_ms.mean
+        returns = rewards[0] + hp.gamma * target * (1 - dones[1:])
+        if ret_ms is not None:                                           # dqn/model.py:262-264: update() reshapes the (E, B) returns with reshape(-1, B)
+            ret_ms.update(returns)
+            returns = (returns - ret_ms.mean) / torch.sqrt(ret_ms.var)
         loss = (chosen - returns.detach()) ** 2
     else:
+        if ret_ms is not None:                                           # dqn/model.py:147-150 ("A E B -> E B A", per-agent statistics)
+            target = (target.permute(1, 2, 0) * torch.sqrt(ret_ms.var) + ret_ms.mean).permute(2, 0, 1)
         returns = rewards + hp.gamma * target * (1 - dones[1:].unsqueeze(0).repeat(N, 1, 1))
+        if ret_ms is not None:                                           # dqn/model.py:154-158
+            r = returns.permute(1, 2, 0)
+            ret_ms.update(r)
+            returns = ((r - ret_ms.mean) / torch.sqrt(ret_ms.var)).permute(2, 0, 1)
         loss = ((chosen - returns.detach()) ** 2).sum(0)
     return (loss * filled).sum() / filled.sum()
 
@@ -206,7 +219,7 @@ def dqn_kink_risk(st: DqnState, batch, hp: DqnHP):
 def dqn_update(st: DqnState, batch, hp: DqnHP):
     """QNetwork.update: returns dict(loss, grad (before clipping), grad_norm)."""
     theta = st.theta.clone().requires_grad_(True)
-    loss = dqn_loss(theta, st.theta_tgt, st.agent_net, st.in_dim, st.out_dim, batch, hp)
+    loss = dqn_loss(theta, st.theta_tgt, st.agent_net, st.in_dim, st.out_dim, batch, hp, st.ret_ms)
     (grad,) = torch.autograd.grad(loss, theta)
     raw = grad.clone()
     norm = torch.linalg.vector_norm(grad)
