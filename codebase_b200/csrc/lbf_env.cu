@@ -25,6 +25,7 @@ struct LbfCfgDev {
   double penalty;
   int RC, pitch, G, D;
   int obs_id, std_rew;   // ObserveID / StandardiseReward wrappers (marlbase/utils/wrappers.py:75-103, 111-141)
+  int upstream_reset;    // marl_lbf_cfg.upstream_reset
 };
 
 struct LbfStateDev {
@@ -65,11 +66,14 @@ struct DrawStream {
   __device__ int randint(int lo, int hi) { return lo + (int)bounded(next(), (uint32_t)(hi - lo)); }
 };
 
+// upstream _is_empty_location: no food on the cell and no player position equal to it.  Default: the players placed so far (positions were cleared);
+// upstream_reset: every player that has a position -- level byte > 0 -- including the not yet re-placed ones of the previous episode.
 __device__ bool cell_empty(const LbfCfgDev& c, const int8_t* f, const uint32_t* pl, int placed, int r, int cc) {
   if (f[r * c.C + cc] != 0) return false;
   const uint32_t want = (uint32_t)r | ((uint32_t)cc << 8);
-  for (int j = 0; j < placed; ++j)
-    if ((pl[j] & 0xFFFFu) == want) return false;
+  const int n = c.upstream_reset ? c.N : placed;
+  for (int j = 0; j < n; ++j)
+    if ((pl[j] & 0xFFFFu) == want && (!c.upstream_reset || ((pl[j] >> 16) & 0xFFu) != 0)) return false;
   return true;
 }
 
@@ -77,7 +81,8 @@ __device__ bool cell_empty(const LbfCfgDev& c, const int8_t* f, const uint32_t* 
 __device__ int reset_env(const LbfCfgDev& c, uint64_t seed, uint32_t gid, uint32_t episode, int8_t* f, uint32_t* pl) {
   DrawStream ds(seed, gid, episode);
   for (int p = 0; p < c.pitch; ++p) f[p] = 0;
-  for (int i = 0; i < c.N; ++i) pl[i] = 0;
+  if (!c.upstream_reset) { for (int i = 0; i < c.N; ++i) pl[i] = 0; }
+  else { for (int k = c.N - 1; k >= 1; --k) (void)ds.randint(0, k + 1); }   // spawn_players: np_random.permutation over the level bounds
   for (int i = 0; i < c.N; ++i) {
     bool placed = false;
     for (int attempts = 0; attempts < 1000 && !placed; ++attempts) {
@@ -104,6 +109,7 @@ __device__ int reset_env(const LbfCfgDev& c, uint64_t seed, uint32_t gid, uint32
     max_lvl = a + (c.N > 1 ? b : 0) + (c.N > 2 ? d : 0);
   }
   const int min_lvl = c.force_coop ? max_lvl : c.minf;
+  if (c.upstream_reset) { for (int k = c.NF - 1; k >= 1; --k) (void)ds.randint(0, k + 1); }   // spawn_food: permutation over the food level bounds
   int count = 0, spawned = 0;
   for (int attempts = 0; count < c.NF && attempts < 1000; ++attempts) {
     const int r = ds.randint(1, c.R - 1), cc = ds.randint(1, c.C - 1);
@@ -509,7 +515,7 @@ static LbfCfgDev to_dev(const marl_lbf_cfg& c) {
   d.penalty = c.penalty;
   d.RC = c.rows * c.cols; d.pitch = (d.RC + 15) & ~15;
   int g = 1; while (g < c.n_agents) g <<= 1;
-  d.obs_id = c.observe_id ? 1 : 0; d.std_rew = c.standardise_rewards ? 1 : 0;
+  d.obs_id = c.observe_id ? 1 : 0; d.std_rew = c.standardise_rewards ? 1 : 0; d.upstream_reset = c.upstream_reset ? 1 : 0;
   d.G = g; d.D = 3 * c.max_num_food + 3 * c.n_agents + (d.obs_id ? c.n_agents : 0);
   return d;
 }

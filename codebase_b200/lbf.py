@@ -36,6 +36,7 @@ class LbfConfig:
     penalty: float = 0.0
     observe_id: int = 0            # env.observe_id: ObserveID wrapper (one-hot agent id in front of every observation)
     standardise_rewards: int = 0   # env.standardise_rewards: StandardiseReward wrapper (per-env running statistics)
+    upstream_reset: int = 0        # 1: upstream's reset details (stale positions block cells, permutation draws consumed), see marl_lbf_cfg
 
     @property
     def obs_dim(self) -> int:

@@ -67,6 +67,10 @@ typedef struct {
   int32_t observe_id;          /* ObserveID wrapper (marlbase/utils/wrappers.py:75-103, env.observe_id): one-hot agent id in front of every observation */
   int32_t standardise_rewards; /* StandardiseReward wrapper (wrappers.py:111-141, env.standardise_rewards): per-env running mean / variance, applied
                                   after RecordEpisodeStatistics (which keeps the raw rewards) and before CooperativeReward (envs.py:97-109) */
+  int32_t upstream_reset;      /* 1: the two reset details of upstream lbforaging that the default leaves out -- (a) players that have not been re-placed
+                                  yet still block their previous episode's cell (upstream never clears positions in reset()), (b) the two
+                                  np_random.permutation() calls over the (identical) level bounds consume random draws (here: n - 1 Philox draws
+                                  each, values unused).  0 (default): positions are cleared first and no draw is spent on the no-op permutations. */
 } marl_lbf_cfg;
 
 typedef struct marl_lbf marl_lbf;

@@ -18,7 +18,7 @@ class OracleCfg(C.Structure):
         ("sight", C.c_int32), ("min_player_level", C.c_int32), ("max_player_level", C.c_int32),
         ("min_food_level", C.c_int32), ("max_food_level", C.c_int32), ("max_episode_steps", C.c_int32),
         ("time_limit", C.c_int32), ("force_coop", C.c_int32), ("normalize_reward", C.c_int32),
-        ("cooperative_reward", C.c_int32), ("penalty", C.c_double), ("observe_id", C.c_int32), ("standardise_rewards", C.c_int32),
+        ("cooperative_reward", C.c_int32), ("penalty", C.c_double), ("observe_id", C.c_int32), ("standardise_rewards", C.c_int32), ("upstream_reset", C.c_int32),
     ]
 
 
@@ -49,7 +49,7 @@ def lib():
 def make_cfg(**kw) -> OracleCfg:
     d = dict(rows=8, cols=8, n_agents=2, max_num_food=3, sight=8, min_player_level=1, max_player_level=2,
              min_food_level=1, max_food_level=0, max_episode_steps=50, time_limit=25, force_coop=0,
-             normalize_reward=1, cooperative_reward=0, penalty=0.0, observe_id=0, standardise_rewards=0)
+             normalize_reward=1, cooperative_reward=0, penalty=0.0, observe_id=0, standardise_rewards=0, upstream_reset=0)
     d.update(kw)
     return OracleCfg(**d)
 

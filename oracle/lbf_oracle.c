@@ -66,8 +66,11 @@ int lbf_oracle_obs_dim(const lbf_oracle_cfg* c) { return 3 * c->max_num_food + 3
 static int is_empty(const lbf_oracle_cfg* cfg, const int8_t* field, const int8_t* players, int placed, int r, int cc) {
   int C = cfg->cols;
   if (F(r, cc) != 0) return 0;
-  for (int j = 0; j < placed; ++j)
-    if (players[4 * j] == r && players[4 * j + 1] == cc) return 0;
+  /* upstream_reset: upstream's _is_empty_location looks at EVERY player that has a position -- reset() never clears positions, so players not yet
+   * re-placed still block their previous episode's cell (level byte 0 = no position yet: first reset) */
+  const int n = cfg->upstream_reset ? cfg->n_agents : placed;
+  for (int j = 0; j < n; ++j)
+    if (players[4 * j] == r && players[4 * j + 1] == cc && (!cfg->upstream_reset || players[4 * j + 2] != 0)) return 0;
   return 1;
 }
 
@@ -76,7 +79,8 @@ void lbf_oracle_reset_one(const lbf_oracle_cfg* cfg, uint64_t seed, uint32_t env
   const int R = cfg->rows, C = cfg->cols, N = cfg->n_agents;
   draw_stream ds; ds_init(&ds, seed, env_gid, episode_idx);
   memset(field, 0, (size_t)R * C);
-  memset(players, 0, (size_t)N * 4);
+  if (!cfg->upstream_reset) memset(players, 0, (size_t)N * 4);
+  else for (int k = N - 1; k >= 1; --k) (void)ds_randint(&ds, 0, k + 1); /* spawn_players: np_random.permutation over the level bounds */
   /* spawn_players: uniform empty cell (<=1000 attempts), then level ~ U[min, max] */
   for (int i = 0; i < N; ++i) {
     int placed = 0;
@@ -106,6 +110,7 @@ void lbf_oracle_reset_one(const lbf_oracle_cfg* cfg, uint64_t seed, uint32_t env
     for (int i = 0; i < N && i < 3; ++i) max_lvl += lv[i];
   }
   int min_lvl = cfg->force_coop ? max_lvl : cfg->min_food_level;
+  if (cfg->upstream_reset) for (int k = cfg->max_num_food - 1; k >= 1; --k) (void)ds_randint(&ds, 0, k + 1); /* spawn_food: permutation over the food level bounds */
   /* spawn_food: interior cells, nothing in the 3x3 neighbourhood, nothing within 2 along row/col, empty */
   int count = 0;
   for (int attempts = 0; count < cfg->max_num_food && attempts < 1000; ++attempts) {

@@ -39,6 +39,7 @@ typedef struct {
   double  penalty;
   int32_t observe_id;          /* ObserveID (wrappers.py:75-103) */
   int32_t standardise_rewards; /* StandardiseReward (wrappers.py:111-141), between RecordEpisodeStatistics and CooperativeReward (envs.py:97-109) */
+  int32_t upstream_reset;      /* 1: stale previous-episode positions block cells during spawning; the two level-bound permutations consume draws */
 } lbf_oracle_cfg;
 
 /* Philox4x32-10 (Random123).  Pinned by the published known-answer vectors in tests/. */

@@ -71,6 +71,7 @@ class LBFConfig:
     penalty: float = 0.0
     observe_id: int = 0
     standardise_rewards: int = 0
+    upstream_reset: int = 0   # 1: stale previous-episode positions block cells while spawning, the level-bound permutations consume draws
 
     @property
     def base_obs_dim(self):
@@ -100,6 +101,8 @@ class ForagingRef:
     def _is_empty(self, row, col, placed):
         if self.field[row, col] != 0:
             return False
+        if self.cfg.upstream_reset:   # upstream _is_empty_location: every player that has a position, re-placed in this reset() or not
+            placed = [p for p in self.players if p.position is not None]
         return all(p.position != (row, col) for p in placed)
 
     def reset(self, seed, env_gid, episode_idx):
@@ -107,21 +110,29 @@ class ForagingRef:
         rng = DrawStream(seed, env_gid, episode_idx)
         self.field[:] = 0
         placed = []
+        if c.upstream_reset:
+            for k in range(c.n_agents - 1, 0, -1):   # spawn_players: np_random.permutation over the (identical) level bounds
+                rng.integers(0, k + 1)
         for p in self.players:
             p.reward = 0.0
-            p.position, p.level = None, c.min_player_level
+            if not c.upstream_reset:
+                p.position = None
+            found = False
             for _ in range(1000):
                 row, col = rng.integers(0, c.rows), rng.integers(0, c.cols)
                 if self._is_empty(row, col, placed):
-                    p.position = (row, col)
+                    p.position, found = (row, col), True
                     p.level = rng.integers(c.min_player_level, c.max_player_level + 1)
                     break
-            if p.position is None:
-                p.position = next((r, q) for r in range(c.rows) for q in range(c.cols) if self._is_empty(r, q, placed))
+            if not found:   # never reached for sane sizes; deterministic fallback shared by the three implementations: first empty cell, min level
+                p.position, p.level = next((r, q) for r in range(c.rows) for q in range(c.cols) if self._is_empty(r, q, placed)), c.min_player_level
             placed.append(p)
         levels = sorted(p.level for p in self.players)
         max_lvl = c.max_food_level if c.max_food_level > 0 else sum(levels[:3])
         min_lvl = max_lvl if c.force_coop else c.min_food_level
+        if c.upstream_reset:
+            for k in range(c.max_num_food - 1, 0, -1):   # spawn_food: np_random.permutation over the food level bounds
+                rng.integers(0, k + 1)
         count = attempts = 0
         while count < c.max_num_food and attempts < 1000:
             attempts += 1

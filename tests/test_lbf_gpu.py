@@ -56,6 +56,7 @@ CONFIGS = [
     (dict(rows=5, cols=5, n_agents=5, max_num_food=2, sight=5, normalize_reward=0), 333),
     (dict(rows=9, cols=12, n_agents=1, max_num_food=1, sight=12, time_limit=7), 65),
     (dict(observe_id=1, standardise_rewards=1), 1500),                                                  # ObserveID + StandardiseReward wrappers
+    (dict(rows=6, cols=6, n_agents=4, max_num_food=3, sight=6, upstream_reset=1), 900),                 # upstream's reset details (stale positions block, permutation draws)
     (dict(rows=10, cols=10, n_agents=3, max_num_food=4, sight=2, penalty=0.1, standardise_rewards=1, cooperative_reward=1, observe_id=1), 500),
 ]
 

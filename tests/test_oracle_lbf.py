@@ -65,11 +65,12 @@ CONFIGS = [
     dict(rows=10, cols=10, n_agents=3, max_num_food=4, sight=2, penalty=0.1, force_coop=1),
     dict(rows=5, cols=5, n_agents=5, max_num_food=2, sight=5, normalize_reward=0),
     dict(observe_id=1, standardise_rewards=1),                                                        # ObserveID + StandardiseReward (wrappers.py:75-141)
+    dict(rows=6, cols=6, n_agents=4, max_num_food=3, sight=6, upstream_reset=1),                      # upstream's reset details on a crowded board
     dict(rows=10, cols=10, n_agents=3, max_num_food=4, sight=2, penalty=0.1, standardise_rewards=1, cooperative_reward=1, observe_id=1),
 ]
 
 
-@pytest.mark.parametrize("cfgkw", CONFIGS, ids=["8x8-2p-3f", "15x15-4p-5f-coopreward", "10x10-3p-4f-2s-coop-pen", "5x5-5p-2f-raw", "8x8-2p-3f-id-stdrew", "10x10-3p-4f-2s-pen-id-stdrew-coopreward"])
+@pytest.mark.parametrize("cfgkw", CONFIGS, ids=["8x8-2p-3f", "15x15-4p-5f-coopreward", "10x10-3p-4f-2s-coop-pen", "5x5-5p-2f-raw", "8x8-2p-3f-id-stdrew", "6x6-4p-3f-upstream-reset", "10x10-3p-4f-2s-pen-id-stdrew-coopreward"])
 def test_c_oracle_matches_python_restatement_on_random_rollouts(cfgkw):
     rng = np.random.default_rng(7)
     ccfg, pcfg, E = lbf_c.make_cfg(**cfgkw), lbf_ref.LBFConfig(**cfgkw), 24
@@ -109,3 +110,27 @@ def test_reset_is_a_pure_function_of_seed_env_and_episode():
         for i in range(3):
             for j in range(i + 1, 3):
                 assert max(abs(rr[i] - rr[j]), abs(cc[i] - cc[j])) > 1
+
+
+def test_upstream_reset_flag_changes_the_draw_stream_and_blocks_stale_cells():
+    """marl_lbf_cfg.upstream_reset: the permutation draws shift the spawn stream (boards differ from the default from the first reset on), and from the
+    second reset on no player is placed on a cell that a not yet re-placed player still occupies from the previous episode."""
+    kw = dict(rows=5, cols=5, n_agents=5, max_num_food=1, sight=5)
+    a = lbf_c.OracleVecEnv(lbf_c.make_cfg(**kw), 256, 5)
+    b = lbf_c.OracleVecEnv(lbf_c.make_cfg(upstream_reset=1, **kw), 256, 5)
+    assert not np.array_equal(a.reset(), b.reset())
+    hits_default = hits_upstream = 0
+    for env, name in ((a, "default"), (b, "upstream")):
+        for _ in range(6):
+            before = env.players.copy()
+            env.reset()
+            after = env.players
+            for e in range(env.E):
+                for i in range(env.N):       # player i was placed while players j > i still stood on their previous cells
+                    for j in range(i + 1, env.N):
+                        if after[e, i, 0] == before[e, j, 0] and after[e, i, 1] == before[e, j, 1]:
+                            if name == "default":
+                                hits_default += 1
+                            else:
+                                hits_upstream += 1
+    assert hits_upstream == 0 and hits_default > 0, (hits_default, hits_upstream)
