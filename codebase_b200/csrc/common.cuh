@@ -96,5 +96,6 @@ int tc_forward_enabled();
 int tc_backward_enabled();
 int tc_pingpong_enabled(int which);   // 0: forward kernels, 1: dH1 kernel
 int tc_onchip_enabled();
+int tc_split_exchange_enabled();
 
 }  // namespace marl

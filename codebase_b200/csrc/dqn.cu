@@ -147,6 +147,8 @@ struct marl_dqn {
   float *tc_h1 = nullptr, *tc_h2 = nullptr, *tc_dh1 = nullptr, *tc_rec = nullptr, *tc_x = nullptr;
   bool tgt_image_current = false;
   unsigned long long* grid_barrier = nullptr; unsigned long long grid_epoch = 0;   // arrival counter of the fused reduce + Adam kernel
+  unsigned long long push_epoch = 0;   // arrival counter of the push kernel (split exchange)
+  bool tq_ahead = false;               // the target forward of the NEXT update has already been launched (between push and finish)
   // gradient exchange over peer memory (several ranks, one process per GPU): own buffer + the peers' buffers opened through CUDA IPC
   XchgParams xchg = {}; float* xbuf = nullptr; void* peer_base[kMaxRanks] = {};
   // online images: valid = a full pack happened and every later change of theta came from adam_kernel (which updates them in place)
@@ -193,7 +195,7 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   rc |= dqn_alloc(&h->tq, rows * cfg->out_dim);
   rc |= dqn_alloc(&h->loss_dev, 8);
   rc |= dqn_alloc(&h->sumsq, (size_t)(h->n_params + 63) / 64 + 1);
-  rc |= dqn_alloc(reinterpret_cast<float**>(&h->grid_barrier), 2);   // one zero-initialised 64-bit counter
+  rc |= dqn_alloc(reinterpret_cast<float**>(&h->grid_barrier), 4);   // two zero-initialised 64-bit counters (grid barrier, push arrivals)
   if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->image), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
@@ -298,9 +300,13 @@ static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* epi
   const RowPlan plan = make_plan(h->ns, batch, T + 1, h->n_sm, min_units);
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 1; src.traj = to_view(traj); src.idx = episode_idx; src.N = h->ns.n_agents; src.D = h->ns.in;
-  // target network on every gathered row (dqn/model.py:132-134)
-  if (int rc = forward_any(h->ns, plan, src, h->theta_tgt, h->image_tgt, h->tq, st, h->tgt_image_current)) return rc;
-  h->tgt_image_current = tc_forward_enabled() != 0;
+  // target network on every gathered row (dqn/model.py:132-134); several ranks: the previous update launched it between its push and its finish
+  if (h->tq_ahead) {
+    h->tq_ahead = false;
+  } else {
+    if (int rc = forward_any(h->ns, plan, src, h->theta_tgt, h->image_tgt, h->tq, st, h->tgt_image_current)) return rc;
+    h->tgt_image_current = tc_forward_enabled() != 0;
+  }
   int n_loss_parts = plan.cta_begin[plan.n_nets];
   const float* td_ext = nullptr;
   float* loss_part = h->loss_part;
@@ -420,6 +426,26 @@ static int dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* ep
   // one kernel for reduce + clip + Adam when its grid fits the GPU in one wave, else the two kernels
   SampleParams sp; memset(&sp, 0, sizeof(sp));
   if (next != nullptr) sp = *next;
+  // Several ranks: the exchange costs a round trip over NVLink (push, flags, poll: 7-10 us per update when exposed).  Split it -- push the local sums
+  // first, then launch the NEXT update's target forward (it needs theta_tgt and the next indices, which the push kernel draws, not this update's Adam
+  // step), then wait for the peers and finish: the wait hides under ~17 us of forward.  Not when this step rewrites theta_tgt.
+  if (h->xchg.world > 1 && tc_split_exchange_enabled()) {
+    if (launch_reduce_push(rp, ap, &h->xchg, sp, h->grid_barrier, &h->push_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) {
+      if (next != nullptr && ap.target_mode == 0 && !h->standardise && h->hp.mixer == 0) {
+        const int T = traj->T;
+        const int min_units = (64 + T) / (T + 1) > 0 ? (64 + T) / (T + 1) : 1;
+        const RowPlan plan = make_plan(h->ns, batch, T + 1, h->n_sm, min_units);
+        RowSource src; memset(&src, 0, sizeof(src));
+        src.mode = 1; src.traj = to_view(traj); src.idx = next->idx; src.N = h->ns.n_agents; src.D = h->ns.in;
+        if (int rc = forward_any(h->ns, plan, src, h->theta_tgt, h->image_tgt, h->tq, (cudaStream_t)stream, h->tgt_image_current)) return rc;
+        h->tgt_image_current = tc_forward_enabled() != 0;
+        h->tq_ahead = true;
+      }
+      if (int rc = launch_adam_finish(rp, ap, &h->xchg, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream)) return rc;
+      if (fused_out) *fused_out = true;
+      return MARL_OK;
+    }
+  }
   if (launch_reduce_adam(rp, ap, &h->xchg, sp, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) {
     if (fused_out) *fused_out = true;
     return MARL_OK;
