@@ -428,7 +428,8 @@ static int dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* ep
   if (next != nullptr) sp = *next;
   // Several ranks: the exchange costs a round trip over NVLink (push, flags, poll: 7-10 us per update when exposed).  Split it -- push the local sums
   // first, then launch the NEXT update's target forward (it needs theta_tgt and the next indices, which the push kernel draws, not this update's Adam
-  // step), then wait for the peers and finish: the wait hides under ~17 us of forward.  Not when this step rewrites theta_tgt.
+  // step), then wait for the peers and finish: the wait hides under ~17 us of forward.  Not when this step rewrites theta_tgt.  Off by default: on two
+  // GPUs the extra launch (prologue, second pass over the Adam state) cost more than the hidden wait saved (120.9 vs 116.8 us per update).
   if (h->xchg.world > 1 && tc_split_exchange_enabled()) {
     if (launch_reduce_push(rp, ap, &h->xchg, sp, h->grid_barrier, &h->push_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) {
       if (next != nullptr && ap.target_mode == 0 && !h->standardise && h->hp.mixer == 0) {
