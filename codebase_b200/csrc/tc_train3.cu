@@ -298,6 +298,16 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd3_kernel(TcTrainParam
     // ---- layer-2 epilogue: the ReLU mask of H2 -> row record; head on the CUDA cores against the FP32 copy of W3 (packed FP32); partial sums of
     // column quarters 1..3 -> shared ------------------------------------------------------------------------------------------------------------
     float q[kOutPad];
+    // target outputs of the next row of the same (agent, episode): requested now, selected in the TD head ~5 k cycles later (they used to be loaded after the
+    // argmax, a dependent global load on the tile's critical path)
+    float tqv[kOutPad];
+#pragma unroll
+    for (int o = 0; o < kOutPad; ++o) tqv[o] = 0.f;
+    if (cq == 0 && r < nrows && tt < T && p.td_ext == nullptr) {
+      const float* tqp = p.tq + (((size_t)agent * B + b) * (T + 1) + tt + 1) * A;
+#pragma unroll
+      for (int o = 0; o < kOutPad; ++o) if (o < A) tqv[o] = tqp[o];
+    }
     {
       uint32_t ra[16], rb[16];
       tmem_ld16_issue(lane_base + d_cur + c0, ra);
@@ -355,15 +365,17 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_dqn_fwd3_kernel(TcTrainParam
             g = p.td_ext[(size_t)agent * p.td_agent_stride + (size_t)b * T + tt];
           } else {
             const float* qn = (r + 1 < nrows) ? (qs + (r + 1) * kOutPad) : carry;
-            const float* tq = p.tq + (((size_t)agent * B + b) * (T + 1) + tt + 1) * A;
             float tsel;
             if (p.double_q) {
               int best = 0; float bv = qn[0];
               for (int o = 1; o < A; ++o) if (qn[o] > bv) { bv = qn[o]; best = o; }
-              tsel = tq[best];
+              tsel = tqv[0];
+#pragma unroll
+              for (int o = 1; o < kOutPad; ++o) tsel = (o == best) ? tqv[o] : tsel;
             } else {
-              tsel = tq[0];
-              for (int o = 1; o < A; ++o) tsel = fmaxf(tsel, tq[o]);
+              tsel = tqv[0];
+#pragma unroll
+              for (int o = 1; o < kOutPad; ++o) if (o < A) tsel = fmaxf(tsel, tqv[o]);
             }
             const float filled = (float)filled_u8, done1 = (float)done1_u8;
             const float y = rew + p.gamma * tsel * (1.f - done1);
@@ -676,7 +688,7 @@ __global__ void __launch_bounds__(kH3Threads, 1) tc_dw2_kernel(TcTrainParams p) 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (t == 0) {
-    mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(full, 4); mbar_init(full + 1, 4);
+    mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(full, 8); mbar_init(full + 1, 8);   // a chunk: 4 warps stage H1, 4 warps dH2
     mbar_init(empty, 1); mbar_init(empty + 1, 1); mbar_init(empty + 2, 1); mbar_init(empty + 3, 1); mbar_init(done, 1);
     fence_mbar_init();
   }
@@ -733,16 +745,21 @@ __global__ void __launch_bounds__(kH3Threads, 1) tc_dw2_kernel(TcTrainParams p) 
     uint8_t* xs = smem + kW3Xs;
     // per tile and row: the record (dLoss/dq[act], act, this thread's H2 mask word), needed when the tile is staged, and this thread's 8 observation
     // columns, needed one tile earlier (layer 1 runs one tile ahead)
+    // A warp may only read its own TMEM lane quarter, so H1 of the chunk (tile, lq) is staged by the four warps of lane quarter lq -- but dH2 comes from
+    // the row records, which any thread can read: the dH2 half of a chunk is staged by the warps of the OTHER pair of lane quarters (lq ^ 2).  All sixteen
+    // warps then work on the chunks of quarters 0 / 1 first and on those of quarters 2 / 3 second, instead of half of them waiting for a buffer.
+    // Per tile and thread: validity of its own row (H1) and the record of the partner row 32 (lq ^ 2) + lane (dLoss/dq[act], act, this thread's H2 mask word).
     struct Rec { bool valid; float g; int act; uint32_t m2; };
+    const int rp = 32 * (lq ^ 2) + lane;
     auto fetch_rec = [&](int vr0, Rec& rc) {
-      rc.valid = false; rc.g = 0.f; rc.act = 0; rc.m2 = 0;
-      if (vr0 + r < row_end) {
+      rc.valid = vr0 + r < row_end; rc.g = 0.f; rc.act = 0; rc.m2 = 0;
+      if (vr0 + rp < row_end) {
         int a, u, o;
-        const size_t d = dst_of3(p.plan, p.src, net, vr0 + r, a, u, o);
-        const float* rp = p.rec + d * kRowRec;
-        const int2 ga = *reinterpret_cast<const int2*>(rp);
-        rc.valid = true; rc.g = __int_as_float(ga.x); rc.act = ga.y;
-        rc.m2 = reinterpret_cast<const uint32_t*>(rp)[8 + cq];
+        const size_t d = dst_of3(p.plan, p.src, net, vr0 + rp, a, u, o);
+        const float* rpp = p.rec + d * kRowRec;
+        const int2 ga = *reinterpret_cast<const int2*>(rpp);
+        rc.g = __int_as_float(ga.x); rc.act = ga.y;
+        rc.m2 = reinterpret_cast<const uint32_t*>(rpp)[8 + cq];
       }
     };
     auto fetch_x = [&](int vr0, float (&x)[8]) {
@@ -784,15 +801,10 @@ __global__ void __launch_bounds__(kH3Threads, 1) tc_dw2_kernel(TcTrainParams p) 
       mbar_wait(bar, parity); parity ^= 1;   // layer 1 of this tile has retired: its accumulator is ready and the X tile is free
       tc_fence_after();
       TSGP(g_ts_dw2, p.dbg, 2, 4 + 3 * tile);
-      if (tile + 1 < n_tiles) {
-        stage_x_and_issue(tile + 1, xn);
-        fetch_rec(row_begin + (tile + 1) * kTileRows, nxt);
-        if (tile + 2 < n_tiles) fetch_x(row_begin + (tile + 2) * kTileRows, xn);
-      }
-      TSGP(g_ts_dw2, p.dbg, 2, 5 + 3 * tile);
-      // dH2[r][j] = g W3[act][j] (H2[r][j] > 0) for this thread's 32 columns
-      float v[32];
-      {
+      // the two halves of a tile: first the chunks of lane quarters 0 / 1 (quarters 0 / 1 stage their H1, quarters 2 / 3 the matching dH2), then the
+      // chunks of quarters 2 / 3 the other way round.  Both times this warp writes buffer lq & 1.
+      auto stage_dh2 = [&]() {   // dH2[r'][j] = g W3[act][j] (H2[r'][j] > 0) for the partner row and this thread's 32 columns
+        float v[32];
         const float4* wrow = w3f4 + cur.act * (kHidden / 4) + 8 * cq;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -801,30 +813,45 @@ __global__ void __launch_bounds__(kH3Threads, 1) tc_dw2_kernel(TcTrainParams p) 
           v[4 * j] = (m & 1u) ? cur.g * w.x : 0.f; v[4 * j + 1] = (m & 2u) ? cur.g * w.y : 0.f;
           v[4 * j + 2] = (m & 4u) ? cur.g * w.z : 0.f; v[4 * j + 3] = (m & 8u) ? cur.g * w.w : 0.f;
         }
-      }
-      // chunk (tile, lq) -> buffer lq & 1; its previous user is chunk (tile, lq - 2) or (tile - 1, lq + 2)
-      if (lq >= 2) mbar_wait(empty + (lq - 2), (uint32_t)tile & 1u);
-      else if (tile > 0) mbar_wait(empty + (lq + 2), (uint32_t)(tile - 1) & 1u);
-      stage_row32(buf, buf + kC3Op, lane, cq, v);
-      {
+        stage_row32(buf, buf + kC3Op, lane, cq, v);
+      };
+      auto stage_h1 = [&]() {   // H1 = relu(accumulator + b1) of this thread's own row (padding rows: zero)
         uint32_t ra[16], rb[16];
         const uint32_t d_col = kColH1 + (uint32_t)(tile & 1) * kHidden;
         tmem_ld16_issue(lane_base + d_col + c0, ra);
         tmem_ld16_issue(lane_base + d_col + c0 + 16, rb);
         tmem_ld_wait(ra);
         tmem_ld_wait(rb);
-        const bool valid = cur.valid;   // padding rows: H1 = relu(b1) would not be zero; their dH2 is (g = 0), zero them anyway
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const uint32_t a = j < 16 ? ra[j & 15] : rb[j & 15];
-          v[j] = valid ? fmaxf(__uint_as_float(a) + b1[c0 + j], 0.f) : 0.f;
+          v[j] = cur.valid ? fmaxf(__uint_as_float(a) + b1[c0 + j], 0.f) : 0.f;
         }
         stage_row32(buf + kW3H1, buf + kW3H1 + kC3Op + kC3Panel, lane, cq, v);
+      };
+      auto publish = [&]() {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(full + (lq & 1));
+      };
+      // first half: chunk (tile, lq & 1); the buffer's previous user was chunk (tile - 1, (lq & 1) + 2)
+      if (tile > 0) mbar_wait(empty + ((lq & 1) + 2), (uint32_t)(tile - 1) & 1u);
+      if (lq < 2) stage_h1(); else stage_dh2();
+      publish();
+      TSGP(g_ts_dw2, p.dbg, 2, 5 + 3 * tile);
+      // between the halves (the tensor core is busy with the first two chunks, whose consumption the second half waits for anyway): the next tile's
+      // X tile and layer 1, the next tile's records, the X columns of the tile after it
+      if (tile + 1 < n_tiles) {
+        stage_x_and_issue(tile + 1, xn);
+        fetch_rec(row_begin + (tile + 1) * kTileRows, nxt);
+        if (tile + 2 < n_tiles) fetch_x(row_begin + (tile + 2) * kTileRows, xn);
       }
+      // second half: chunk (tile, (lq & 1) + 2); previous user: chunk (tile, lq & 1)
+      mbar_wait(empty + (lq & 1), (uint32_t)tile & 1u);
+      if (lq < 2) stage_dh2(); else stage_h1();
+      publish();
       TSGP(g_ts_dw2, p.dbg, 2, 6 + 3 * tile);
       cur = nxt;
     }
