@@ -138,9 +138,36 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
   TSG(g_ts_forward, 2);
   int ts_tile = 0; (void)ts_tile;
 
-  for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows) {
+  // Two accumulator blocks alternate between tiles (TMEM: A hi | A lo | D0 | D1): the head of tile k - 1 (CUDA cores) runs under the layer-2 MMAs of tile k.
+  auto head_tile = [&](uint32_t d_col, size_t dst, int nr) {
+    // layer-2 epilogue + head: relu(D + b2) of this thread's 32 columns against the FP32 copy of W3; the partial sums of column quarters 1..3 travel
+    // through shared memory and column quarter 0 adds them in a fixed order
+    uint32_t ra[16], rb[16];
+    tmem_ld16_issue(lane_base + d_col + c0, ra);
+    tmem_ld16_issue(lane_base + d_col + c0 + 16, rb);
+    tmem_ld_wait(ra);
+    tmem_ld_wait(rb);
+    float q[kOutPad];
+    head_partial(ra, rb, b2 + c0, w3f + (c0 >> 2), out, q);
+    if (cq > 0) {
+      float4* pp = reinterpret_cast<float4*>(part + ((size_t)(cq - 1) * kTileRows + r) * kOutPad);
+      pp[0] = make_float4(q[0], q[1], q[2], q[3]); pp[1] = make_float4(q[4], q[5], q[6], q[7]);
+    }
+    named_bar_sync(1 + lq, 128);   // the four warps of this lane quarter
+    if (cq == 0 && r < nr) {
+      float* dstp = p.out + dst * out;
+#pragma unroll
+      for (int o = 0; o < kOutPad; ++o)
+        if (o < out) dstp[o] = (((q[o] + part[((size_t)0 * kTileRows + r) * kOutPad + o]) + part[((size_t)1 * kTileRows + r) * kOutPad + o]) + part[((size_t)2 * kTileRows + r) * kOutPad + o]) + b3[o];
+    }
+    // the next head's partials are written at least two __syncthreads later: no second barrier needed
+  };
+  int k = 0, prev_nrows = 0;
+  size_t prev_dst = 0;
+  for (int vr0 = row_begin; vr0 < row_end; vr0 += kTileRows, ++k) {
     const int nrows = min(kTileRows, row_end - vr0);
     const bool has_next = vr0 + kTileRows < row_end;
+    const uint32_t d_cur = (k & 1) ? kColD1 : kColD0, d_prev = (k & 1) ? kColD0 : kColD1;
     if (has_next) fetch_a(vr0 + kTileRows, min(kTileRows, row_end - vr0 - kTileRows), key_nxt, dst_next);
     // ---- input row -> A operand (hi / lo), zero padded to k1steps * 8 features -----------------------------------
     if (x_active) {
@@ -158,7 +185,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
     // ---- layer 1 -------------------------------------------------------------------------------------------------
     if (t == 0) {
       tc_fence_after();
-      issue_layer<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
+      issue_layer<kMaxObsDim / 8, kHidden, kPanelBytes>(tmem, d_cur, smem_base + kOffW1Hi, smem_base + kOffW1Lo, k1steps);
       mma_commit(bar);
     }
     mbar_wait(bar, parity); parity ^= 1;
@@ -168,8 +195,8 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
     {
       const float* bias = b1 + c0;
       uint32_t ra[16], rb[16];
-      tmem_ld16_issue(lane_base + kColD + c0, ra);
-      tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
+      tmem_ld16_issue(lane_base + d_cur + c0, ra);
+      tmem_ld16_issue(lane_base + d_cur + c0 + 16, rb);
       tmem_ld_wait(ra);
       tmem_ld_wait(rb);
 #pragma unroll
@@ -191,40 +218,18 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
       TSG(g_ts_forward, 5 + 6 * ts_tile);
       if (t == 0) {
         tc_fence_after();
-        issue_layer<kHidden / 8, kHidden, kPanelBytes>(tmem, kColD, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
+        issue_layer<kHidden / 8, kHidden, kPanelBytes>(tmem, d_cur, smem_base + kOffW2Hi, smem_base + kOffW2Lo, kHidden / 8);
         mma_commit(bar);
       }
-      // prefetch the next tile's rows under the layer-2 MMAs (the longest stretch in which the CUDA cores idle); the episode index they hang
-      // off was requested at the top of this tile
+      // under the layer-2 MMAs (the longest stretch in which the CUDA cores would idle): the next tile's rows are requested (the episode index they
+      // hang off was requested at the top of this tile), and the previous tile's head runs on its accumulator block
       if (has_next) fetch_b(key_nxt, xnext);
+      if (k > 0) head_tile(d_prev, prev_dst, prev_nrows);
       mbar_wait(bar, parity); parity ^= 1;
       tc_fence_after();
       TSG(g_ts_forward, 6 + 6 * ts_tile);
     }
-    // ---- layer-2 epilogue + head on the CUDA cores: relu(D + b2) of this thread's 32 columns against the FP32 copy of W3; the partial sums of
-    // column quarters 1..3 travel through shared memory and column quarter 0 adds them in a fixed order ------------------------------------
-    {
-      uint32_t ra[16], rb[16];
-      tmem_ld16_issue(lane_base + kColD + c0, ra);
-      tmem_ld16_issue(lane_base + kColD + c0 + 16, rb);
-      tmem_ld_wait(ra);
-      tmem_ld_wait(rb);
-      float q[kOutPad];
-      head_partial(ra, rb, b2 + c0, w3f + (c0 >> 2), out, q);
-      if (cq > 0) {
-        float4* pp = reinterpret_cast<float4*>(part + ((size_t)(cq - 1) * kTileRows + r) * kOutPad);
-        pp[0] = make_float4(q[0], q[1], q[2], q[3]); pp[1] = make_float4(q[4], q[5], q[6], q[7]);
-      }
-      named_bar_sync(1 + lq, 128);   // the four warps of this lane quarter
-      TSG(g_ts_forward, 7 + 6 * ts_tile);
-      if (cq == 0 && r < nrows) {
-        float* dst = p.out + dst_row * out;
-#pragma unroll
-        for (int o = 0; o < kOutPad; ++o)
-          if (o < out) dst[o] = (((q[o] + part[((size_t)0 * kTileRows + r) * kOutPad + o]) + part[((size_t)1 * kTileRows + r) * kOutPad + o]) + part[((size_t)2 * kTileRows + r) * kOutPad + o]) + b3[o];
-      }
-      // the next tile's partials are written two __syncthreads later: no second barrier needed
-    }
+    prev_dst = dst_row; prev_nrows = nrows;
     TSG(g_ts_forward, 8 + 6 * ts_tile);
     ts_tile += 1;
     dst_row = dst_next;
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
     // the next tile's first MMAs write D / read A only after the __syncthreads that follows its operand staging, by which time
     // every warp has finished reading this tile's accumulators
   }
+  head_tile(((k - 1) & 1) ? kColD1 : kColD0, prev_dst, prev_nrows);   // the last tile's head
   tc_fence_before();
   __syncthreads();
   TSG(g_ts_forward, 30);
