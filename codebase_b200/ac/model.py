@@ -23,8 +23,6 @@ class A2CNetwork:
                 raise NotImplementedError(f"{name}.use_rnn=True (GRU) is out of scope of the B200 hot path")
             if list(part.layers) != [HIDDEN, HIDDEN]:
                 raise NotImplementedError(f"{name}.layers={list(part.layers)}: the fused kernels implement the shipped [128, 128] MLP only")
-        if critic.centralised:
-            raise NotImplementedError("critic.centralised=True (MAA2C) is not implemented on the B200 path yet")
         opt = getattr(cfg, "optimizer", "Adam")
         if (opt if isinstance(opt, str) else opt.__name__) != "Adam":
             raise NotImplementedError("only optimizer=Adam is implemented")
@@ -36,6 +34,12 @@ class A2CNetwork:
         if len(set(obs_dims)) != 1 or len(set(act_dims)) != 1:
             raise NotImplementedError("agents with different observation / action sizes are not implemented")
         self.in_dim, self.n_actions = obs_dims[0], act_dims[0]
+        # critic.centralised (MAA2C / MAPPO, ac/model.py:62-65): every agent's critic reads the concatenation of all agents' observations
+        self.centralised = bool(critic.centralised) and self.n_agents > 1
+        self.critic_in = self.n_agents * self.in_dim if self.centralised else self.in_dim
+        if self.critic_in > 32:
+            raise NotImplementedError(f"critic.centralised: the joint observation is {self.critic_in} wide; the learner kernels stage at most 32 input features "
+                                      "(2 agents on Foraging-8x8-2p-3f: 30)")
         self.gamma, self.entropy_coef, self.n_steps = float(cfg.gamma), float(cfg.entropy_coef), int(cfg.n_steps)
         self.grad_clip, self.value_loss_coef = cfg.grad_clip, float(cfg.value_loss_coef)
         self.target_update_interval_or_tau = float(cfg.target_update_interval_or_tau)
@@ -48,7 +52,7 @@ class A2CNetwork:
         self.max_T = int(max_episode_length or 500)
         self._lib = nat.lib()
         acfg = nat.MlpCfg(self.n_agents, self.n_actor_nets, (C.c_int32 * 32)(*self.actor_net), self.in_dim, HIDDEN, self.n_actions)
-        ccfg = nat.MlpCfg(self.n_agents, self.n_critic_nets, (C.c_int32 * 32)(*self.critic_net), self.in_dim, HIDDEN, 1)
+        ccfg = nat.MlpCfg(self.n_agents, self.n_critic_nets, (C.c_int32 * 32)(*self.critic_net), self.critic_in, HIDDEN, 1)
         hp = nat.A2cHP(float(cfg.lr), self.gamma, float(self.grad_clip or 0.0), self.n_steps, self.entropy_coef, self.value_loss_coef,
                        self.target_update_interval_or_tau, 0.9, 0.999, 1e-8)
         self._h = C.c_void_p()
@@ -65,7 +69,7 @@ class A2CNetwork:
         self.adam_m, self.adam_v = nat.device_view(ptrs[2].value, n, self.device), nat.device_view(ptrs[3].value, n, self.device)
         self.grad = nat.device_view(ptrs[4].value, n + 4, self.device)
         self.theta[: self.n_actor].copy_(init_flat_params(self.n_actor_nets, self.in_dim, self.n_actions, actor.use_orthogonal_init))
-        self.theta[self.n_actor:].copy_(init_flat_params(self.n_critic_nets, self.in_dim, 1, critic.use_orthogonal_init))
+        self.theta[self.n_actor:].copy_(init_flat_params(self.n_critic_nets, self.critic_in, 1, critic.use_orthogonal_init))
         self.soft_update(1.0)
         self._metrics = torch.zeros(6, dtype=torch.float32, device=self.device)
         self.standardise_returns = bool(getattr(cfg, "standardise_returns", False))   # ac/model.py:112-114
@@ -114,7 +118,7 @@ class A2CNetwork:
         return out
 
     def values(self, obs: torch.Tensor, target: bool = False) -> torch.Tensor:
-        """get_value (ac/model.py:155-163): obs f32[E,N,D] -> f32[E,N]."""
+        """get_value (ac/model.py:155-163): obs f32[E,N,D] -> f32[E,N] (centralised critic: each agent's network reads all N x D values of its env)."""
         E = obs.shape[0]
         out = torch.empty(E, self.n_agents, 1, dtype=torch.float32, device=self.device)
         nat.check(self._lib.marl_a2c_forward_critic(self._h, nat.ptr(obs), C.c_int32(E), C.c_int32(int(target)), nat.ptr(out), nat.stream_ptr()), "marl_a2c_forward_critic")
@@ -168,8 +172,8 @@ class A2CNetwork:
     def state_dict(self):
         th, tg = self.theta.detach().cpu(), self.theta_tgt.detach().cpu()
         sd = flat_to_state_dict(th[: self.n_actor], f"actor.{self._akind}", self.n_actor_nets, self.in_dim, self.n_actions)
-        sd.update(flat_to_state_dict(th[self.n_actor:], f"critic.{self._ckind}", self.n_critic_nets, self.in_dim, 1))
-        sd.update(flat_to_state_dict(tg, f"target_critic.{self._ckind}", self.n_critic_nets, self.in_dim, 1))
+        sd.update(flat_to_state_dict(th[self.n_actor:], f"critic.{self._ckind}", self.n_critic_nets, self.critic_in, 1))
+        sd.update(flat_to_state_dict(tg, f"target_critic.{self._ckind}", self.n_critic_nets, self.critic_in, 1))
         return sd
 
     def load_state_dict(self, sd):

@@ -70,6 +70,17 @@ __global__ void mean_metrics_kernel(const float* per_epoch, int n_epochs, float*
   out[k] = k == 4 ? per_epoch[4] : s / (float)n_epochs;   // [4] = filled count (the same every epoch)
 }
 
+// centralised critic (ac/model.py:62-65,156-157): the joint observation of every (env, step) = the agents' observations side by side
+struct JointParams { TrajView traj; const int32_t* idx; int P; float* out; };   // out: [P][T+1][N * D]
+__global__ void joint_obs_kernel(JointParams p) {
+  const int T1 = p.traj.T + 1, ND = p.traj.N * p.traj.D;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)p.P * T1 * ND) return;
+  const int c = (int)(i % ND), t = (int)((i / ND) % T1), b = (int)(i / ((size_t)ND * T1));
+  const int j = c / p.traj.D, d = c - j * p.traj.D;
+  p.out[i] = p.traj.obs[(((size_t)p.idx[b] * p.traj.N + j) * T1 + t) * p.traj.D + d];
+}
+
 __global__ void iota_kernel(int32_t* x, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = i;
@@ -93,6 +104,7 @@ struct marl_a2c {
   float *logits_all = nullptr, *old_logp = nullptr, *epoch_metrics = nullptr;   // PPO (allocated on first use)
   // standardise_returns: RunningMeanStd(shape=(n_agents,)) -- mean[N] | var[N] (float32), count (a Python float in the reference), partial sums
   int standardise = 0; float* ret_ms = nullptr; double* ret_count = nullptr; double* ret_part = nullptr;
+  int centralised = 0; float* joint = nullptr;   // critic.centralised: joint observations of the batch [P][T+1][N * D]
 };
 constexpr int kMaxPpoEpochs = 64;
 
@@ -103,7 +115,7 @@ int marl_a2c_destroy(marl_a2c* h) {
   cudaSetDevice(h->device);
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch); cudaFree(h->loss_part);
   cudaFree(h->vt); cudaFree(h->ret); cudaFree(h->adv); cudaFree(h->metrics); cudaFree(h->idx); cudaFree(h->image);
-  cudaFree(h->logits_all); cudaFree(h->old_logp); cudaFree(h->epoch_metrics); cudaFree(h->ret_ms); cudaFree(h->ret_count); cudaFree(h->ret_part);
+  cudaFree(h->logits_all); cudaFree(h->old_logp); cudaFree(h->epoch_metrics); cudaFree(h->ret_ms); cudaFree(h->ret_count); cudaFree(h->ret_part); cudaFree(h->joint);
   delete h;
   return MARL_OK;
 }
@@ -113,7 +125,8 @@ int marl_a2c_create(const marl_mlp_cfg* actor, const marl_mlp_cfg* critic, const
   *out = nullptr;
   if (int rc = check_mlp_cfg(actor, "marl_a2c_create(actor)")) return rc;
   if (int rc = check_mlp_cfg(critic, "marl_a2c_create(critic)")) return rc;
-  MARL_REQUIRE(actor->n_agents == critic->n_agents && actor->in_dim == critic->in_dim, "marl_a2c_create: actor / critic shapes differ (a centralised critic is not implemented)");
+  MARL_REQUIRE(actor->n_agents == critic->n_agents && (actor->in_dim == critic->in_dim || critic->in_dim == actor->n_agents * actor->in_dim),
+               "marl_a2c_create: the critic's input width must be the actor's (%d) or, for a centralised critic, n_agents x it (%d)", actor->in_dim, actor->n_agents * actor->in_dim);
   MARL_REQUIRE(critic->out_dim == 1, "marl_a2c_create: the critic outputs one state value per agent");
   MARL_REQUIRE(max_envs >= 1 && max_T >= 1, "marl_a2c_create: max_envs/max_T must be >= 1");
   MARL_REQUIRE(hp->n_steps >= 1 && hp->n_steps <= kMaxNStep, "marl_a2c_create: n_steps %d out of range (1..%d)", hp->n_steps, kMaxNStep);
@@ -121,6 +134,7 @@ int marl_a2c_create(const marl_mlp_cfg* actor, const marl_mlp_cfg* critic, const
   marl_a2c* h = new marl_a2c();
   h->actor = to_netset(actor); h->critic = to_netset(critic);
   h->hp = *hp; h->device = device; h->max_envs = max_envs; h->max_T = max_T;
+  h->centralised = (critic->in_dim != actor->in_dim || (actor->n_agents == 1 && false)) ? 1 : 0;
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); h->n_sm = prop.multiProcessorCount;
   h->n_actor = (int64_t)actor->n_nets * h->actor.lay.P; h->n_critic = (int64_t)critic->n_nets * h->critic.lay.P; h->n_params = h->n_actor + h->n_critic;
   const int pmax = h->actor.lay.P > h->critic.lay.P ? h->actor.lay.P : h->critic.lay.P;
@@ -135,7 +149,9 @@ int marl_a2c_create(const marl_mlp_cfg* actor, const marl_mlp_cfg* critic, const
   rc |= dev_alloc_zero(reinterpret_cast<float**>(&h->image), (size_t)(actor->n_nets > critic->n_nets ? actor->n_nets : critic->n_nets) * tc_image_bytes() / 4 + 4);
   if (rc) { marl_a2c_destroy(h); return MARL_ENOMEM; }
   iota_kernel<<<(max_envs + 255) / 256, 256>>>(h->idx, max_envs);
+  if (h->centralised && dev_alloc_zero(&h->joint, (size_t)max_envs * (max_T + 1) * critic->in_dim)) { marl_a2c_destroy(h); return MARL_ENOMEM; }
   if (int rc2 = learner_kernels_init(actor->in_dim)) { marl_a2c_destroy(h); return rc2; }
+  if (int rc2 = learner_kernels_init(critic->in_dim)) { marl_a2c_destroy(h); return rc2; }
   if (int rc2 = tc_forward_init()) { marl_a2c_destroy(h); return rc2; }
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("marl_a2c_create: device error during setup"); marl_a2c_destroy(h); return MARL_ECUDA; }
   *out = h;
@@ -168,6 +184,7 @@ static int a2c_dense_forward(marl_a2c* h, const NetSet& ns, const float* theta, 
   const RowPlan plan = make_plan(ns, n_envs, 1, h->n_sm, 32);
   RowSource src; memset(&src, 0, sizeof(src));
   src.mode = 0; src.dense = obs; src.E = n_envs; src.N = ns.n_agents; src.D = ns.in;
+  if (ns.in != h->actor.in) { src.mode = 3; src.joint = obs; }   // centralised critic: obs float[E][N][D] read as the joint rows float[E][N * D]
   return forward_any(ns, plan, src, theta, h->image, out, (cudaStream_t)stream);
 }
 
@@ -183,7 +200,7 @@ int marl_a2c_forward_critic(marl_a2c* h, const float* obs, int32_t n_envs, int32
   return a2c_dense_forward(h, h->critic, use_target ? h->theta_tgt : h->theta + h->n_actor, obs, n_envs, values_out, stream);
 }
 
-struct A2cPass { RowSource src; RowPlan cplan, aplan; };
+struct A2cPass { RowSource src, csrc; RowPlan cplan, aplan; };   // csrc: the critic's rows (== src unless the critic is centralised)
 
 // target-critic pass + n-step returns (ac/model.py:190-201): everything of an update that does not depend on the trainable parameters
 static int a2c_prepare(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs, cudaStream_t st, A2cPass& ps) {
@@ -198,8 +215,16 @@ static int a2c_prepare(marl_a2c* h, const marl_traj_view* batch, int32_t n_envs,
   ps.src.mode = 1; ps.src.traj = to_view(batch); ps.src.idx = h->idx; ps.src.N = N; ps.src.D = h->actor.in;
   ps.cplan = make_plan(h->critic, n_envs, T + 1, h->n_sm, min_units);
   ps.aplan = make_plan(h->actor, n_envs, T + 1, h->n_sm, min_units);
+  ps.csrc = ps.src;
+  if (h->centralised) {   // get_value (ac/model.py:156-157): every agent's critic reads the concatenated observations
+    JointParams jp; jp.traj = ps.src.traj; jp.idx = h->idx; jp.P = n_envs; jp.out = h->joint;
+    const size_t n = (size_t)n_envs * (T + 1) * h->critic.in;
+    joint_obs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(jp);
+    MARL_CUDA_TRY(cudaGetLastError());
+    ps.csrc.mode = 2; ps.csrc.joint = h->joint; ps.csrc.D = h->critic.in;
+  }
   // 1. target critic on all T+1 observations (ac/model.py:190-193)
-  if (int rc = forward_any(h->critic, ps.cplan, ps.src, h->theta_tgt, h->image, h->vt, st)) return rc;
+  if (int rc = forward_any(h->critic, ps.cplan, ps.csrc, h->theta_tgt, h->image, h->vt, st)) return rc;
   // 2. n-step returns (ac/model.py:198-201)
   NStepParams np; np.vt = h->vt; np.traj = ps.src.traj; np.idx = h->idx; np.N = N; np.P = n_envs; np.n_steps = h->hp.n_steps; np.ret = h->ret;
   np.ret_ms = h->standardise ? h->ret_ms : nullptr;
@@ -242,7 +267,7 @@ int marl_a2c_ret_ms_ptrs(marl_a2c* h, float** ret_ms, double** count) {
 static int a2c_gradients(marl_a2c* h, const A2cPass& ps, cudaStream_t st, const float* old_logp, float ppo_clip) {
   // 3. critic: forward, value loss, backward; leaves advantage = returns - V for the actor pass
   TrainParams tp; memset(&tp, 0, sizeof(tp));
-  tp.plan = ps.cplan; tp.src = ps.src; tp.theta = h->theta + h->n_actor; tp.lay = h->critic.lay; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch;
+  tp.plan = ps.cplan; tp.src = ps.csrc; tp.theta = h->theta + h->n_actor; tp.lay = h->critic.lay; tp.scratch = h->scratch; tp.scratch_pitch = h->scratch_pitch;
   tp.loss_part = h->loss_part; tp.returns = h->ret; tp.adv_out = h->adv; tp.value_coef = h->hp.value_loss_coef;
   if (int rc = launch_train(tp, kHeadA2cCritic, st)) return rc;
   ReduceParams rp; memset(&rp, 0, sizeof(rp));  // (sumsq_part stays NULL: two passes write different gradient slices)
@@ -251,7 +276,7 @@ static int a2c_gradients(marl_a2c* h, const A2cPass& ps, cudaStream_t st, const 
   rp.n_loss_parts = ps.cplan.cta_begin[ps.cplan.n_nets]; rp.grad = h->grad + h->n_actor; rp.stats = h->grad + h->n_params; rp.stats_accumulate = 0;
   if (int rc = launch_grad_reduce(rp, st)) return rc;
   // 4. actor: forward, log-softmax, policy-gradient (or clipped surrogate) + entropy loss, backward
-  tp.plan = ps.aplan; tp.theta = h->theta; tp.lay = h->actor.lay; tp.adv = h->adv; tp.entropy_coef = h->hp.entropy_coef;
+  tp.plan = ps.aplan; tp.src = ps.src; tp.theta = h->theta; tp.lay = h->actor.lay; tp.adv = h->adv; tp.entropy_coef = h->hp.entropy_coef;
   tp.old_logp = old_logp; tp.ppo_clip = ppo_clip;
   if (int rc = launch_train(tp, kHeadA2cActor, st)) return rc;
   rp.n_nets = h->actor.n_nets; rp.P = h->actor.lay.P; memcpy(rp.cta_begin, ps.aplan.cta_begin, sizeof(rp.cta_begin));

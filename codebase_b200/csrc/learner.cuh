@@ -25,10 +25,16 @@ struct RowPlan {
 };
 
 struct RowSource {
-  int mode;  // 0: dense obs float[E][N][D];  1: gather from the trajectory store through episode indices
+  // 0: dense obs float[E][N][D];  1: gather from the trajectory store through episode indices;
+  // 2 / 3: JOINT observation rows float[units][unit_rows][D] shared by all agents (centralised critic, ac/model.py:62-65,156-157: every agent's critic
+  //        sees the concatenation of all agents' observations; D = their total width): 2 = outputs laid out like mode 1 ([agent][unit][row], loss
+  //        scalars from the trajectory store), 3 = like mode 0 ([unit][agent]; `joint` is then simply the dense obs array read as [E][N * D_agent])
+  int mode;
   const float* dense; int E, N, D;
   TrajView traj; const int32_t* idx;  // idx[B] ring slots (device)
+  const float* joint;
 };
+__host__ __device__ __forceinline__ bool src_dense_out(int mode) { return mode == 0 || mode == 3; }
 
 __device__ __forceinline__ void cta_rows(const RowPlan& p, int& net, int& row_begin, int& row_end) {
   net = 0;
@@ -50,6 +56,7 @@ __device__ __forceinline__ void decode_row(const RowPlan& p, int net, int vr, in
 
 __device__ __forceinline__ const float* row_ptr(const RowSource& s, int agent, int unit, int off) {
   if (s.mode == 0) return s.dense + ((size_t)unit * s.N + agent) * s.D;
+  if (s.mode >= 2) return s.joint + ((size_t)unit * (s.mode == 2 ? s.traj.T + 1 : 1) + off) * s.D;   // (unit_rows: T + 1 when training, 1 for plain inference)
   const size_t ep = (size_t)s.idx[unit];
   return s.traj.obs + ((ep * s.traj.N + agent) * (size_t)(s.traj.T + 1) + off) * s.traj.D;
 }
@@ -75,10 +82,12 @@ __device__ __forceinline__ void setup_rows(RowMeta* m, const RowPlan& p, const R
     decode_row(p, net, vr0 + r, agent, unit, off);
     if (s.mode == 0) {
       src = s.dense + ((size_t)unit * s.N + agent) * s.D;
+    } else if (s.mode == 3) {
+      src = s.joint + ((size_t)unit * p.unit_rows + off) * s.D;
     } else {
       const size_t ep = (size_t)s.idx[unit];
       const TrajView& tv = s.traj;
-      src = tv.obs + ((ep * tv.N + agent) * (size_t)(tv.T + 1) + off) * tv.D;
+      src = s.mode == 2 ? s.joint + ((size_t)unit * p.unit_rows + off) * s.D : tv.obs + ((ep * tv.N + agent) * (size_t)(tv.T + 1) + off) * tv.D;
       if (kWithScalars && off < tv.T) {
         act = tv.act[(ep * tv.N + agent) * tv.T + off];
         rew = tv.rew[(ep * tv.N + agent) * tv.T + off];

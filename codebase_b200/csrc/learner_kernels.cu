@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(FwdParams p
       const int r = i / p.lay.out, o = i - r * p.lay.out;
       int agent, unit, off;
       decode_row(p.plan, net, vr0 + r, agent, unit, off);
-      const size_t dst = p.src.mode == 0 ? ((size_t)unit * p.src.N + agent)
+      const size_t dst = src_dense_out(p.src.mode) ? ((size_t)unit * p.src.N + agent)
                                          : (((size_t)agent * p.plan.units_per_agent + unit) * p.plan.unit_rows + off);
       p.out[dst * p.lay.out + o] = Q[r * kOutPad + o];
     }

@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
     k.agent = 0; k.unit = 0; k.off = 0; k.ep = 0; k.valid = r < nrows;
     if (k.valid) {
       decode_row(p.plan, net, vr0 + r, k.agent, k.unit, k.off);
-      dst = p.src.mode == 0 ? ((size_t)k.unit * p.src.N + k.agent) : (((size_t)k.agent * p.plan.units_per_agent + k.unit) * p.plan.unit_rows + k.off);
-      if (p.src.mode != 0) k.ep = p.src.idx[k.unit];
+      dst = src_dense_out(p.src.mode) ? ((size_t)k.unit * p.src.N + k.agent) : (((size_t)k.agent * p.plan.units_per_agent + k.unit) * p.plan.unit_rows + k.off);
+      if (p.src.mode == 1) k.ep = p.src.idx[k.unit];
     }
   };
   auto fetch_b = [&](const RowKey& k, float (&x)[8]) {
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kTrThreads, 1) tc_forward_kernel(FwdParams p, 
     if (k.valid && x_active) {
       const TrajView& tv = p.src.traj;
       const float* src = p.src.mode == 0 ? p.src.dense + ((size_t)k.unit * p.src.N + k.agent) * D
-                                         : tv.obs + (((size_t)k.ep * tv.N + k.agent) * (size_t)(tv.T + 1) + k.off) * D;
+                         : p.src.mode == 1 ? tv.obs + (((size_t)k.ep * tv.N + k.agent) * (size_t)(tv.T + 1) + k.off) * D
+                                           : p.src.joint + ((size_t)k.unit * p.plan.unit_rows + k.off) * D;   // joint rows (centralised critic)
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = (8 * cq + j < D) ? src[8 * cq + j] : 0.f;
     }
@@ -562,7 +563,7 @@ int launch_pack_weights(const float* theta, const NetLayout& lay, int n_nets, ui
 }
 
 int launch_tc_forward(const FwdParams& p, const uint8_t* images, cudaStream_t st) {
-  if (tc_pingpong_enabled(0)) MARL_CUDA_TRY(launch_pdl(tc_forward2_kernel, dim3(p.plan.cta_begin[p.plan.n_nets]), dim3(kP2Threads), kP2Smem, st, p, images));
+  if (tc_pingpong_enabled(0) && p.src.mode < 2) MARL_CUDA_TRY(launch_pdl(tc_forward2_kernel, dim3(p.plan.cta_begin[p.plan.n_nets]), dim3(kP2Threads), kP2Smem, st, p, images));
   else MARL_CUDA_TRY(launch_pdl(tc_forward_kernel, dim3(p.plan.cta_begin[p.plan.n_nets]), dim3(kTrThreads), kTcSmemBytes, st, p, images));
   return MARL_OK;
 }

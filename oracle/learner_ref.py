@@ -351,6 +351,13 @@ class A2CState:
     v: dict = field(default_factory=dict)
     steps: int = 0             # optimiser steps taken
     ret_ms: object = None      # RunningMeanStdRef(shape=(n_agents,)) when cfg.standardise_returns (ac/model.py:112-114), else None
+    centralised: bool = False  # critic.centralised (ac/model.py:62-65,156-157): every agent's critic reads the concatenated observations
+
+    def critic_inputs(self, obs):
+        """get_value's inputs: the per-agent list, or n_agents x the concatenation (and the matching input width)"""
+        if not self.centralised:
+            return obs, self.in_dim
+        return len(obs) * [torch.cat(obs, dim=-1)], len(obs) * self.in_dim
 
     def __post_init__(self):
         for k in ("actor", "critic"):
@@ -362,8 +369,9 @@ def a2c_losses(actor, critic, target, st: A2CState, batch, hp: A2CHP):
     """batch = dict(obss (T+1,P,N*D), actions (T,P,N) i64, rewards (T,P,N), dones (T+1,P) f32/bool, filled (T,P))"""
     N, D = len(st.actor_net), st.in_dim
     obs = list(torch.split(batch["obss"], D, dim=-1))
+    cobs, CD = st.critic_inputs(obs)
     with torch.no_grad():
-        next_value = torch.cat(agents_forward(target, st.critic_net, obs, D, 1), dim=-1)                  # (T+1,P,N)
+        next_value = torch.cat(agents_forward(target, st.critic_net, cobs, CD, 1), dim=-1)                # (T+1,P,N)
     if st.ret_ms is not None:                                                                             # ac/model.py:195-196
         next_value = next_value * torch.sqrt(st.ret_ms.var) + st.ret_ms.mean
     done = batch["dones"].float().unsqueeze(-1).repeat(1, 1, N)
@@ -372,7 +380,7 @@ def a2c_losses(actor, critic, target, st: A2CState, batch, hp: A2CHP):
         st.ret_ms.update(returns)
         returns = (returns - st.ret_ms.mean) / torch.sqrt(st.ret_ms.var)
     obs_t = [o[:-1] for o in obs]
-    values = torch.cat(agents_forward(critic, st.critic_net, obs_t, D, 1), dim=-1)                       # (T,P,N)
+    values = torch.cat(agents_forward(critic, st.critic_net, [o[:-1] for o in cobs], CD, 1), dim=-1)     # (T,P,N)
     logits = agents_forward(actor, st.actor_net, obs_t, D, st.n_actions)
     logp_all = [F.log_softmax(l, dim=-1) for l in logits]
     acts = batch["actions"]
@@ -393,8 +401,10 @@ def ppo_update(st: A2CState, batch, hp: A2CHP, step: int, num_epochs: int = 4, p
     obs = list(torch.split(batch["obss"], D, dim=-1))
     obs_t = [o[:-1] for o in obs]
     acts, filled = batch["actions"], batch["filled"]
+    cobs, CD = st.critic_inputs(obs)
+    cobs_t = [o[:-1] for o in cobs]
     with torch.no_grad():
-        next_value = torch.cat(agents_forward(st.target, st.critic_net, obs, D, 1), dim=-1)
+        next_value = torch.cat(agents_forward(st.target, st.critic_net, cobs, CD, 1), dim=-1)
         if st.ret_ms is not None:                                                                         # ac/model.py:272-273
             next_value = next_value * torch.sqrt(st.ret_ms.var) + st.ret_ms.mean
         done = batch["dones"].float().unsqueeze(-1).repeat(1, 1, N)
@@ -409,7 +419,7 @@ def ppo_update(st: A2CState, batch, hp: A2CHP, step: int, num_epochs: int = 4, p
     for _ in range(num_epochs):
         actor = st.actor.clone().requires_grad_(True)
         critic = st.critic.clone().requires_grad_(True)
-        values = torch.cat(agents_forward(critic, st.critic_net, obs_t, D, 1), dim=-1)
+        values = torch.cat(agents_forward(critic, st.critic_net, cobs_t, CD, 1), dim=-1)
         logp_all = [F.log_softmax(l, dim=-1) for l in agents_forward(actor, st.actor_net, obs_t, D, st.n_actions)]
         logp = torch.cat([lp.gather(-1, acts[..., i:i + 1]) for i, lp in enumerate(logp_all)], dim=-1)
         entropy = torch.stack([-(lp.exp() * lp).sum(-1) for lp in logp_all], dim=-1).sum(-1)

@@ -70,6 +70,34 @@ def test_oracle_standardise_returns_matches_live_reference(cls):
 
 
 @pytest.mark.refsrc
+@pytest.mark.parametrize("cls", ["A2CNetwork", "PPONetwork"])
+def test_oracle_centralised_critic_matches_live_reference(cls):
+    """critic.centralised=True (MAA2C / MAPPO, ac/model.py:62-65,156-157): oracle vs the live classes"""
+    from collections import namedtuple
+
+    from oracle import ref_shim
+
+    ref = ref_shim.load()
+    torch.manual_seed(4)
+    cfg = ref_shim.a2c_cfg(num_epochs=3, ppo_clip=0.2, target_update_interval_or_tau=2)
+    model = getattr(ref.ac_model, cls)([ref_shim.Space(shape=(D,))] * N, [ref_shim.Space(n=A)] * N, cfg, ref_shim.net_cfg(), ref_shim.net_cfg(centralised=True), "cpu")
+    sd = model.state_dict()
+    assert sd["critic.independent.0.network.0.weight"].shape == (128, N * D)
+    st = lr.A2CState(lr.flat_from_state_dict(sd, "actor.independent", N), lr.flat_from_state_dict(sd, "critic.independent", N),
+                     lr.flat_from_state_dict(sd, "target_critic.independent", N), [0, 1], [0, 1], D, A, centralised=True)
+    hp = lr.A2CHP(target_update_interval_or_tau=2)
+    Batch = namedtuple("Batch", ["obss", "actions", "rewards", "dones", "filled", "action_masks"])
+    rng = np.random.default_rng(5)
+    for step in (0, 2, 3):
+        b = _oracle_batch(_batch_arrays(rng, 10, N))
+        want = model.update(Batch(b["obss"], b["actions"], b["rewards"], b["dones"].bool(), b["filled"], None), step)
+        got = lr.ppo_update(st, b, hp, step, 3, 0.2) if cls == "PPONetwork" else lr.a2c_update(st, b, hp, step)
+        _close([got[k] for k in ("loss", "actor_loss", "value_loss", "entropy")], [want[k] for k in ("loss", "actor_loss", "value_loss", "entropy")])
+    d = np.abs(st.critic.numpy() - lr.flat_from_state_dict(model.state_dict(), "critic.independent", N).numpy())
+    assert np.quantile(d, 0.999) < 1e-5
+
+
+@pytest.mark.refsrc
 @pytest.mark.parametrize("sharing,clip", [(False, False), (True, 0.5)])
 def test_oracle_ppo_matches_live_reference(sharing, clip):
     """three PPO updates (4 epochs each) of the reference's PPONetwork vs oracle.learner_ref.ppo_update from the same weights and batches"""
@@ -112,14 +140,15 @@ def test_oracle_ppo_first_epoch_is_a2c_with_unit_ratio():
     _close(g_ppo["actor"].numpy(), g_a2c["actor"].numpy()); _close(g_ppo["critic"].numpy(), g_a2c["critic"].numpy())
 
 
-def _model(sharing, hp, P, n_agents, num_epochs, ppo_clip, standardise=False, cls="PPONetwork"):
+def _model(sharing, hp, P, n_agents, num_epochs, ppo_clip, standardise=False, cls="PPONetwork", centralised=False):
     from codebase_b200.ac import model as M
 
     cfg = types.SimpleNamespace(optimizer="Adam", lr=hp.lr, gamma=hp.gamma, grad_clip=hp.grad_clip, n_steps=hp.n_steps, entropy_coef=hp.entropy_coef,
                                 value_loss_coef=hp.value_loss_coef, target_update_interval_or_tau=hp.target_update_interval_or_tau, standardise_returns=standardise,
                                 num_epochs=num_epochs, ppo_clip=ppo_clip)
     net = types.SimpleNamespace(layers=[128, 128], parameter_sharing=sharing, use_rnn=False, use_orthogonal_init=True, centralised=False)
-    return getattr(M, cls)([_space(shape=(D,))] * n_agents, [_space(n=A)] * n_agents, cfg, net, net, "cuda", max_envs=P, max_episode_length=T)
+    cnet = types.SimpleNamespace(layers=[128, 128], parameter_sharing=sharing, use_rnn=False, use_orthogonal_init=True, centralised=centralised)
+    return getattr(M, cls)([_space(shape=(D,))] * n_agents, [_space(n=A)] * n_agents, cfg, net, cnet, "cuda", max_envs=P, max_episode_length=T)
 
 
 @pytest.mark.gpu
@@ -182,6 +211,39 @@ def test_standardise_returns_matches_oracle(cls):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cls,sharing", [("A2CNetwork", False), ("PPONetwork", True)])
+def test_centralised_critic_matches_oracle(cls, sharing):
+    """MAA2C / MAPPO on the device: the critic passes read the joint observation rows (source mode 2; `values()`: mode 3)"""
+    from codebase_b200.lbf import TrajStore
+
+    P, n_agents, epochs = 300, 2, 2
+    rng = np.random.default_rng(31)
+    hp = lr.A2CHP(target_update_interval_or_tau=2)
+    m = _model(sharing, hp, P, n_agents, epochs, 0.2, cls=cls, centralised=True)
+    nets = [0, 0] if sharing else [0, 1]
+    assert m.n_critic == len(set(nets)) * lr.net_size(n_agents * D, 1)
+    st = lr.A2CState(m.theta[: m.n_actor].cpu().clone(), m.theta[m.n_actor:].cpu().clone(), m.theta_tgt.cpu().clone(), nets, nets, D, A, centralised=True)
+    obs = rng.integers(-1, 8, size=(77, n_agents, D)).astype(np.float32)
+    joint = torch.tensor(obs.reshape(77, n_agents * D))
+    want_v = torch.cat(lr.agents_forward(st.critic, nets, [joint] * n_agents, n_agents * D, 1), -1).numpy()
+    _close(m.values(torch.tensor(obs, device="cuda")).cpu().numpy(), want_v)
+    for u, step in enumerate((0, 2, 5)):
+        s = _batch_arrays(rng, P, n_agents)
+        want = lr.ppo_update(st, _oracle_batch(s), hp, step, epochs, 0.2) if cls == "PPONetwork" else lr.a2c_update(st, _oracle_batch(s), hp, step)
+        ts = TrajStore(P, n_agents, T, D, m.device)
+        for k in ("obs", "act", "rew", "done", "filled"):
+            getattr(ts, k).copy_(torch.as_tensor(s[k]))
+        met = m.metrics_dict(m.update_from_store(ts, P, step))
+        _close([met["loss"], met["actor_loss"], met["value_loss"], met["entropy"]], [want["loss"], want["actor_loss"], want["value_loss"], want["entropy"]], rtol=2e-5, atol=2e-5)
+        d = np.abs(m.theta.cpu().numpy() - np.concatenate([st.actor.numpy(), st.critic.numpy()]))
+        assert np.quantile(d, 0.999) < 1e-5, (u, np.quantile(d, 0.999))
+        m.theta.copy_(torch.cat([st.actor, st.critic])); m.theta_tgt.copy_(st.target)
+        m.adam_m.copy_(torch.cat([st.m["actor"], st.m["critic"]])); m.adam_v.copy_(torch.cat([st.v["actor"], st.v["critic"]]))
+    sd = m.state_dict()
+    assert sd["critic." + ("networks" if sharing else "independent") + ".0.network.0.weight"].shape == (128, n_agents * D)
+
+
+@pytest.mark.gpu
 def test_ippo_driver_runs_and_logs(tmp_path, monkeypatch):
     """ac.train.main with +algorithm=ippo end to end: results.csv has the reference's AC columns"""
     import pandas as pd
@@ -195,3 +257,18 @@ def test_ippo_driver_runs_and_logs(tmp_path, monkeypatch):
     for col in ("environment_steps", "actor_loss", "entropy", "value_loss", "loss", "mean_episode_returns", "updates"):
         assert col in df.columns, col
     assert len(df) >= 3 and df["environment_steps"].is_monotonic_increasing
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["maa2c", "mappo"])
+def test_centralised_critic_drivers_run_and_log(tmp_path, monkeypatch, alg):
+    """+algorithm=maa2c / mappo (critic.centralised: True) end to end on the 2-agent task whose joint observation (30) fits the kernels' 32 input features"""
+    import pandas as pd
+
+    from codebase_b200 import run
+
+    monkeypatch.chdir(tmp_path)
+    run.main([f"+algorithm={alg}", "env.name=lbforaging:Foraging-8x8-2p-3f-v3", "env.time_limit=25", "env.parallel_envs=256", "seed=2",
+              "algorithm.total_steps=30000", "algorithm.eval_interval=10000", f"run_dir={tmp_path}/out"])
+    df = pd.read_csv(tmp_path / "out" / "results.csv")
+    assert len(df) >= 2 and np.isfinite(df["value_loss"].iloc[-1]) and df["environment_steps"].is_monotonic_increasing
