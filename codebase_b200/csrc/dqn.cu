@@ -5,6 +5,7 @@
 // draw + gather (marlbase/dqn/train.py:94-124).
 #include "learner.cuh"
 #include "retms.cuh"
+#include "qmix.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -160,6 +161,9 @@ struct marl_dqn {
   bool timing = false; std::vector<cudaEvent_t> ev; int ev_used = 0; bool ev_split = false;
   // cfg.standardise_returns: RunningMeanStd over the TD targets (mean[n] | var[n], count, partial sums, returns / chosen-Q scratch)
   int standardise = 0, n_stat = 0; float *ret_ms = nullptr, *ret = nullptr, *chosen = nullptr; double *ret_count = nullptr, *ret_part = nullptr;
+  // QMIX (hp.mixer == 2): the mixing network's parameters / Adam state / gradient (+ 4 statistics), per-sample records, chunked partial sums, tile list
+  QmixLayout ql = {}; float *mix = nullptr, *mix_tgt = nullptr, *mix_m = nullptr, *mix_v = nullptr, *mix_grad = nullptr, *mix_rec = nullptr, *mix_part = nullptr;
+  QmixTile* mix_tiles = nullptr; int mix_n_tiles = 0;
 };
 static const int kTimingPairs = 1024;
 
@@ -175,7 +179,7 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   MARL_REQUIRE(cfg->hidden == kHidden, "marl_dqn_create: only layers=[128,128] is implemented on the B200 path (got hidden=%d)", cfg->hidden);
   MARL_REQUIRE(cfg->out_dim >= 1 && cfg->out_dim <= kOutPad, "marl_dqn_create: n_actions %d not supported (1..%d)", cfg->out_dim, kOutPad);
   MARL_REQUIRE(max_batch >= 1 && max_T >= 1, "marl_dqn_create: max_batch/max_T must be >= 1");
-  MARL_REQUIRE(hp->mixer == 0 || hp->mixer == 1, "marl_dqn_create: mixer must be 0 (independent) or 1 (VDN)");
+  MARL_REQUIRE(hp->mixer >= 0 && hp->mixer <= 2, "marl_dqn_create: mixer must be 0 (independent), 1 (VDN) or 2 (QMIX)");
   for (int a = 0; a < cfg->n_agents; ++a) MARL_REQUIRE(cfg->agent_net[a] >= 0 && cfg->agent_net[a] < cfg->n_nets, "marl_dqn_create: agent_net[%d] out of range", a);
   if (int rc = check_device(device)) return rc;
   marl_dqn* h = new marl_dqn();
@@ -197,6 +201,7 @@ int marl_dqn_create(const marl_mlp_cfg* cfg, const marl_dqn_hp* hp, int32_t max_
   rc |= dqn_alloc(&h->sumsq, (size_t)(h->n_params + 63) / 64 + 1);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->grid_barrier), 4);   // two zero-initialised 64-bit counters (grid barrier, push arrivals)
   if (hp->mixer == 1) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)max_batch * max_T); }
+  if (hp->mixer == 2) { rc |= dqn_alloc(&h->q_all, rows * cfg->out_dim); rc |= dqn_alloc(&h->td, (size_t)cfg->n_agents * max_batch * max_T); }
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->idx), max_batch);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->image), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->image_tgt), (size_t)cfg->n_nets * tc_image_bytes() / 4 + 4);
@@ -214,6 +219,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
   cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec); cudaFree(h->tc_x); cudaFree(h->grid_barrier);
   for (int r = 0; r < kMaxRanks; ++r) if (h->peer_base[r] != nullptr && r != h->xchg.rank) cudaIpcCloseMemHandle(h->peer_base[r]);
+  cudaFree(h->mix); cudaFree(h->mix_tgt); cudaFree(h->mix_m); cudaFree(h->mix_v); cudaFree(h->mix_grad); cudaFree(h->mix_rec); cudaFree(h->mix_part); cudaFree(h->mix_tiles);
   cudaFree(h->xbuf); cudaFree(h->ret_ms); cudaFree(h->ret); cudaFree(h->chosen); cudaFree(h->ret_count); cudaFree(h->ret_part);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
@@ -224,6 +230,7 @@ int marl_dqn_destroy(marl_dqn* h) {
  * kernels above); mean 0, var 1, count 1e-4 on first enable. */
 int marl_dqn_standardise_returns(marl_dqn* h, int32_t enable) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_standardise_returns: NULL handle");
+  MARL_REQUIRE(h->hp.mixer != 2 || !enable, "marl_dqn_standardise_returns: not implemented for QMIX (qmix.yaml inherits standardise_returns: False)");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   if (enable && !h->ret_ms) {
     const int n = h->hp.mixer == 1 ? h->max_batch : h->ns.n_agents, C = h->hp.mixer == 1 ? 1 : h->ns.n_agents;
@@ -253,6 +260,42 @@ int marl_dqn_ret_ms_ptrs(marl_dqn* h, float** ret_ms, double** count, int32_t* n
   return MARL_OK;
 }
 
+/* QMixNetwork.__init__ (dqn/model.py:365-379): the mixing network over the concatenated observations (state_dim = N * in_dim).  Parameters are
+ * initialised by the caller through marl_dqn_qmix_ptrs (nn.Linear defaults), then marl_dqn_sync_target copies them to the target mixer. */
+int marl_dqn_qmix_init(marl_dqn* h, int32_t embed_dim, int32_t hypernet_layers, int32_t hypernet_embed) {
+  MARL_REQUIRE(h != nullptr && h->hp.mixer == 2, "marl_dqn_qmix_init: the learner was not created with mixer = 2");
+  MARL_REQUIRE(h->mix == nullptr, "marl_dqn_qmix_init: already initialised");
+  MARL_REQUIRE(hypernet_layers == 2, "marl_dqn_qmix_init: hypernet_layers = %d: only the shipped two-layer hypernetworks (qmix.yaml) are implemented", hypernet_layers);
+  MARL_REQUIRE(embed_dim >= 4 && embed_dim <= kQmixEmbedMax && embed_dim % 4 == 0, "marl_dqn_qmix_init: embed_dim %d not supported (multiple of 4, <= %d)", embed_dim, kQmixEmbedMax);
+  MARL_REQUIRE(hypernet_embed >= 4 && hypernet_embed <= kQmixHypMax && hypernet_embed % 4 == 0, "marl_dqn_qmix_init: hypernet_embed %d not supported (multiple of 4, <= %d)", hypernet_embed, kQmixHypMax);
+  const int N = h->ns.n_agents, S = N * h->ns.in;
+  MARL_REQUIRE(S <= kQmixStateMax && N * embed_dim <= kQmixNEMax, "marl_dqn_qmix_init: state_dim %d (<= %d) or n_agents x embed_dim %d (<= %d) too large", S, kQmixStateMax, N * embed_dim, kQmixNEMax);
+  MARL_CUDA_TRY(cudaSetDevice(h->device));
+  h->ql = qmix_layout(N, S, embed_dim, hypernet_embed);
+  const size_t n = (size_t)h->ql.n, samples = (size_t)h->max_batch * h->max_T;
+  MARL_REQUIRE(n * sizeof(float) <= 200 * 1024, "marl_dqn_qmix_init: the mixer's %zu parameters do not fit shared memory", n);
+  std::vector<QmixTile> tiles(kQmixMaxTiles);
+  const int nt = qmix_tiles(h->ql, tiles.data());
+  MARL_REQUIRE(nt > 0, "marl_dqn_qmix_init: too many weight-gradient tiles");
+  int rc = 0;
+  rc |= dqn_alloc(&h->mix, n); rc |= dqn_alloc(&h->mix_tgt, n); rc |= dqn_alloc(&h->mix_m, n); rc |= dqn_alloc(&h->mix_v, n); rc |= dqn_alloc(&h->mix_grad, n + 4);
+  rc |= dqn_alloc(&h->mix_rec, (size_t)h->ql.R * samples); rc |= dqn_alloc(&h->mix_part, (size_t)kQmixChunks * n);
+  rc |= dqn_alloc(reinterpret_cast<float**>(&h->mix_tiles), (size_t)nt * sizeof(QmixTile) / 4);
+  cudaFree(h->loss_part); h->loss_part = nullptr;   // one block of statistics per kQmixThreads samples
+  rc |= dqn_alloc(&h->loss_part, 4 * ((size_t)h->n_sm + samples / kQmixThreads + 2));
+  if (rc) return MARL_ENOMEM;
+  MARL_CUDA_TRY(cudaMemcpy(h->mix_tiles, tiles.data(), (size_t)nt * sizeof(QmixTile), cudaMemcpyHostToDevice));
+  h->mix_n_tiles = nt;
+  MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * sizeof(float))));
+  return MARL_OK;
+}
+int marl_dqn_qmix_ptrs(marl_dqn* h, float** mix, float** mix_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params) {
+  MARL_REQUIRE(h != nullptr && h->mix != nullptr, "marl_dqn_qmix_ptrs: no mixer (marl_dqn_qmix_init)");
+  if (mix) *mix = h->mix; if (mix_tgt) *mix_tgt = h->mix_tgt; if (adam_m) *adam_m = h->mix_m; if (adam_v) *adam_v = h->mix_v;
+  if (grad) *grad = h->mix_grad; if (n_params) *n_params = h->ql.n;
+  return MARL_OK;
+}
+
 int marl_dqn_param_ptrs(marl_dqn* h, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_param_ptrs: NULL handle");
   if (theta) *theta = h->theta; if (theta_tgt) *theta_tgt = h->theta_tgt; if (adam_m) *adam_m = h->m; if (adam_v) *adam_v = h->v;
@@ -264,6 +307,7 @@ int marl_dqn_sync_target(marl_dqn* h, void* stream) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_sync_target: NULL handle");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   MARL_CUDA_TRY(cudaMemcpyAsync(h->theta_tgt, h->theta, h->n_params * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (h->mix) MARL_CUDA_TRY(cudaMemcpyAsync(h->mix_tgt, h->mix, (size_t)h->ql.n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));   // dqn/model.py:438-443
   h->tgt_image_current = false;
   return MARL_OK;
 }
@@ -344,6 +388,23 @@ static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* epi
     MARL_CUDA_TRY(cudaGetLastError());
     n_loss_parts += vb;
     td_ext = h->td;
+  } else if (h->hp.mixer == 2) {  // QMIX: the mixer turns the agents' Q-values into the TD error and hands dL/dq_a back per agent (qmix.cuh)
+    MARL_REQUIRE(h->mix != nullptr, "marl_dqn_update: QMIX needs marl_dqn_qmix_init first");
+    if (int rc = forward_any(h->ns, plan, src, h->theta, h->image, h->q_all, st, h->image_current)) return rc;
+    h->image_current = tc_forward_enabled() != 0;
+    QmixParams qp; memset(&qp, 0, sizeof(qp));
+    qp.L = h->ql; qp.q = h->q_all; qp.tq = h->tq; qp.traj = src.traj; qp.idx = episode_idx; qp.B = batch; qp.A = h->ns.out; qp.D = h->ns.in;
+    qp.gamma = h->hp.gamma; qp.double_q = h->hp.double_q; qp.mix = h->mix; qp.mix_tgt = h->mix_tgt; qp.rec = h->mix_rec; qp.td = h->td;
+    qp.loss_part = h->loss_part + 4 * (size_t)n_loss_parts;
+    const int Sn = batch * T, qb = (Sn + kQmixThreads - 1) / kQmixThreads, n = h->ql.n;
+    qmix_mix_kernel<<<qb, kQmixThreads, (size_t)n * sizeof(float), st>>>(qp);
+    const int chunk_len = (((Sn + kQmixChunks - 1) / kQmixChunks) + 31) & ~31, chunks = (Sn + chunk_len - 1) / chunk_len;
+    qmix_wgrad_kernel<<<dim3(h->mix_n_tiles, chunks), 256, 0, st>>>(h->mix_rec, Sn, h->mix_tiles, chunk_len, h->mix_part, n);
+    qmix_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->mix_part, chunks, n, h->mix_grad, qp.loss_part, qb);
+    MARL_CUDA_TRY(cudaGetLastError());
+    n_loss_parts += qb;
+    td_ext = h->td;
+    td_agent_stride = batch * T;
   }
   TrainParams tp; memset(&tp, 0, sizeof(tp));
   tp.plan = plan; tp.src = src; tp.theta = h->theta; tp.lay = h->ns.lay; tp.tq = h->tq; tp.td_ext = td_ext; tp.td_agent_stride = td_agent_stride;
@@ -406,12 +467,23 @@ static void dqn_adam_params(marl_dqn* h, float* loss_out, AdamParams& ap) {
   }
 }
 
+// QMIX: the mixer's share of the single Adam step (same step count, learning rate and target update as the agents' networks; no clipping:
+// clip_grad_norm_ covers self.critic.parameters() only, dqn/model.py:169-170)
+static int qmix_adam(marl_dqn* h, const AdamParams& main, cudaStream_t st) {
+  if (h->hp.mixer != 2) return MARL_OK;
+  AdamParams ap = main;
+  ap.theta = h->mix; ap.theta_tgt = h->mix_tgt; ap.m = h->mix_m; ap.v = h->mix_v; ap.grad = h->mix_grad; ap.n = h->ql.n; ap.tgt_begin = 0; ap.tgt_n = h->ql.n;
+  ap.grad_clip = 0.f; ap.loss_out = nullptr; ap.sumsq_part = nullptr; ap.n_sumsq = 0; ap.image = nullptr; ap.bwd_image = nullptr; ap.img_nets = 0;
+  return launch_adam(ap, st);
+}
+
 int marl_dqn_update_apply(marl_dqn* h, float* loss_out, void* stream) {
   MARL_REQUIRE(h != nullptr, "marl_dqn_update_apply: NULL handle");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   AdamParams ap;
   dqn_adam_params(h, loss_out, ap);
-  return launch_adam(ap, (cudaStream_t)stream);
+  if (int rc = launch_adam(ap, (cudaStream_t)stream)) return rc;
+  return qmix_adam(h, ap, (cudaStream_t)stream);
 }
 
 // one update; `next` (optional): replay indices of the following update, drawn inside the fused tail kernel; *fused_out says whether it was
@@ -449,11 +521,12 @@ static int dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* ep
   }
   if (launch_reduce_adam(rp, ap, &h->xchg, sp, h->grid_barrier, &h->grid_epoch, h->n_sm, (cudaStream_t)stream) == MARL_OK) {
     if (fused_out) *fused_out = true;
-    return MARL_OK;
+    return qmix_adam(h, ap, (cudaStream_t)stream);
   }
   MARL_REQUIRE(h->xchg.world <= 1, "marl_dqn_update: the peer-memory exchange needs the fused tail kernel (parameter count too large for one wave)");
   if (int rc = launch_grad_reduce(rp, (cudaStream_t)stream)) return rc;
-  return launch_adam(ap, (cudaStream_t)stream);
+  if (int rc = launch_adam(ap, (cudaStream_t)stream)) return rc;
+  return qmix_adam(h, ap, (cudaStream_t)stream);
 }
 
 int marl_dqn_update(marl_dqn* h, const marl_traj_view* traj, const int32_t* episode_idx, int32_t batch, float* loss_out, void* stream) {
@@ -555,6 +628,7 @@ int marl_dqn_peer_attach(marl_dqn* h, int32_t rank, int32_t world, const void* h
   MARL_REQUIRE(h != nullptr && handles != nullptr, "marl_dqn_peer_attach: NULL argument");
   MARL_REQUIRE(world >= 2 && world <= kMaxRanks && rank >= 0 && rank < world, "marl_dqn_peer_attach: rank %d / world %d out of range (2..%d ranks)", rank, world, kMaxRanks);
   MARL_REQUIRE(h->xbuf != nullptr && h->xchg.world <= 1, "marl_dqn_peer_attach: call marl_dqn_peer_handle first, attach once");
+  MARL_REQUIRE(h->hp.mixer != 2, "marl_dqn_peer_attach: the mixer's gradient is not part of the peer exchange: QMIX runs on one GPU");
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   {  // the exchange lives inside the fused reduce + Adam kernel: refuse here, before any update mutates counters, when that kernel cannot
      // cover this parameter count with one co-resident wave (a later fallback to the two-kernel tail would dead-lock the peers' polls)

@@ -272,3 +272,71 @@ class VDNetwork(QNetwork):
     """marlbase/dqn/model.py:199-269: Q_tot = sum_i Q_i, reward of agent 0 (CooperativeReward makes them equal)."""
 
     mixer = 1
+
+
+MIXER_KEYS = ("hyper_w_1.0", "hyper_w_1.2", "hyper_w_final.0", "hyper_w_final.2", "hyper_b_1", "V.0", "V.2")
+
+
+def mixer_shapes(n_agents, state_dim, embed_dim, hypernet_embed):
+    """(out, in) of the mixing network's seven Linear layers in the reference's state_dict order (dqn/model.py:283-311, hypernet_layers == 2)."""
+    N, S, E, He = n_agents, state_dim, embed_dim, hypernet_embed
+    return ((He, S), (N * E, He), (He, S), (E, He), (E, S), (E, S), (1, E))
+
+
+class QMixNetwork(QNetwork):
+    """marlbase/dqn/model.py:343-443: the agents' Q-values of the chosen (target: double-Q) actions go through a monotonic mixing network conditioned
+    on the state (all observations concatenated); one Adam over critic + mixer, the gradient clip covers the critic only, target updates include
+    the mixer.  The mixer runs in qmix.cuh's kernels next to the tensor-core training pass of the agents' networks (csrc/dqn.cu, mixer == 2)."""
+
+    mixer = 2
+
+    def __init__(self, obs_space, action_space, cfg, layers, parameter_sharing, use_rnn, use_orthogonal_init, mixing, device, max_batch=None, max_episode_length=None):
+        if bool(getattr(cfg, "standardise_returns", False)):
+            raise NotImplementedError("standardise_returns with QMIX is not implemented (qmix.yaml inherits standardise_returns: False)")
+        super().__init__(obs_space, action_space, cfg, layers, parameter_sharing, use_rnn, use_orthogonal_init, device, max_batch, max_episode_length)
+        mixing = dict(mixing)
+        self.embed_dim, self.hypernet_embed = int(mixing["embed_dim"]), int(mixing["hypernet_embed"])
+        self.state_dim = self.n_agents * self.in_dim
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.marl_dqn_qmix_init(self._h, C.c_int32(self.embed_dim), C.c_int32(int(mixing["hypernet_layers"])), C.c_int32(self.hypernet_embed)), "marl_dqn_qmix_init")
+        ptrs = [C.c_void_p() for _ in range(5)]
+        n = C.c_int64()
+        nat.check(self._lib.marl_dqn_qmix_ptrs(self._h, *[C.byref(p) for p in ptrs], C.byref(n)), "marl_dqn_qmix_ptrs")
+        self.n_mix = int(n.value)
+        self.mix, self.mix_tgt, self.mix_m, self.mix_v = [nat.device_view(p.value, self.n_mix, self.device) for p in ptrs[:4]]
+        self.mix_grad = nat.device_view(ptrs[4].value, self.n_mix + 4, self.device)
+        # QMixer's layers are plain nn.Linear (PyTorch's default initialisation), created in this order (dqn/model.py:283-311)
+        parts = []
+        for (o, i) in mixer_shapes(self.n_agents, self.state_dim, self.embed_dim, self.hypernet_embed):
+            lin = torch.nn.Linear(i, o)
+            parts += [lin.weight.data.reshape(-1), lin.bias.data.reshape(-1)]
+        self.mix.copy_(torch.cat(parts).float())
+        self.hard_update()
+
+    def _mixer_sd(self, flat, prefix):
+        sd, o = {}, 0
+        for k, (no, ni) in zip(MIXER_KEYS, mixer_shapes(self.n_agents, self.state_dim, self.embed_dim, self.hypernet_embed)):
+            sd[f"{prefix}.{k}.weight"] = flat[o:o + no * ni].view(no, ni).clone(); o += no * ni
+            sd[f"{prefix}.{k}.bias"] = flat[o:o + no].clone(); o += no
+        return sd
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd.update(self._mixer_sd(self.mix.detach().cpu(), "mixer"))
+        sd.update(self._mixer_sd(self.mix_tgt.detach().cpu(), "target_mixer"))
+        return sd
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        for dst, prefix in ((self.mix, "mixer"), (self.mix_tgt, "target_mixer")):
+            dst.copy_(torch.cat([sd[f"{prefix}.{k}.{p}"].reshape(-1).float() for k in MIXER_KEYS for p in ("weight", "bias")]))
+
+    def parameters(self):
+        return [self.theta, self.mix]
+
+    def attach_peers(self, group=None):
+        raise NotImplementedError("QMIX runs on one GPU: the mixer's gradient is not part of the peer-memory exchange")
+
+    def close(self):
+        super().close()
+        self.mix = self.mix_tgt = self.mix_m = self.mix_v = self.mix_grad = None

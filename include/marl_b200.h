@@ -175,7 +175,7 @@ typedef struct {
   int32_t double_q;                       /* idqn.yaml:21 */
   float   target_update_interval_or_tau;  /* idqn.yaml:37: > 1 hard update every k updates, < 1 Polyak tau */
   float   beta1, beta2, eps;              /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 (dqn/model.py:71) */
-  int32_t mixer;                          /* 0 = independent learners (QNetwork), 1 = VDN sum (VDNetwork) */
+  int32_t mixer;                          /* 0 = independent learners (QNetwork), 1 = VDN sum (VDNetwork), 2 = QMIX (QMixNetwork) */
 } marl_dqn_hp;
 
 typedef struct marl_dqn marl_dqn;
@@ -190,6 +190,14 @@ int marl_dqn_destroy(marl_dqn* q);
  * batch's returns, the returns are standardised before the loss.  One column per agent; VDN: one per batch entry (the reference's reshape). */
 int marl_dqn_standardise_returns(marl_dqn* q, int32_t enable);
 int marl_dqn_ret_ms_ptrs(marl_dqn* q, float** ret_ms /* mean[n] | var[n] */, double** count, int32_t* n_stat);
+/* QMixNetwork (marlbase/dqn/model.py:272-443, configs/algorithm/qmix.yaml): with hp.mixer == 2, call once after marl_dqn_create.  The mixing
+ * network (hypernet_layers == 2) works on state = the agents' observations concatenated (state_dim = n_agents * in_dim); its parameters are one flat
+ * vector in the reference's state_dict order: hyper_w_1.0, hyper_w_1.2, hyper_w_final.0, hyper_w_final.2, hyper_b_1, V.0, V.2 (weight, bias each).
+ * marl_dqn_qmix_ptrs exposes parameters / target / Adam state / gradient (+ 4 statistics); initialise `mix` through it (nn.Linear defaults are the
+ * caller's job), then marl_dqn_sync_target.  marl_dqn_update* then train agents and mixer with the one Adam step of the reference (the gradient
+ * clip covers the agents' networks only, dqn/model.py:169-170); target updates (hard / Polyak) include the mixer (433-443). */
+int marl_dqn_qmix_init(marl_dqn* q, int32_t embed_dim, int32_t hypernet_layers, int32_t hypernet_embed);
+int marl_dqn_qmix_ptrs(marl_dqn* q, float** mix, float** mix_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params);
 int marl_dqn_param_ptrs(marl_dqn* q, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad,
                         int64_t* n_params);
 int marl_dqn_sync_target(marl_dqn* q, void* stream);        /* hard_update (dqn/model.py:195-196) */

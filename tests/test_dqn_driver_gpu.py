@@ -10,7 +10,7 @@ IDQN_COLS = ["environment_steps", "agent0/mean_episode_returns", "agent0/std_epi
              "loss", "mean_episode_length", "mean_episode_returns", "mean_episode_time", "std_episode_length", "std_episode_returns", "std_episode_time", "updates"]
 
 
-@pytest.mark.parametrize("alg", ["idqn", "vdn"])
+@pytest.mark.parametrize("alg", ["idqn", "vdn", "qmix"])
 def test_driver_writes_reference_schema(tmp_path, monkeypatch, alg):
     from codebase_b200 import run
 

@@ -39,7 +39,7 @@ def test_shipped_overlays_are_not_degenerate():
     from codebase_b200.config import compose
     from codebase_b200.dqn.train import check_iteration_budget
 
-    for algo in ("idqn", "vdn", "ia2c"):
+    for algo in ("idqn", "vdn", "qmix", "ia2c"):
         cfg = compose([f"+algorithm={algo}", "env.name=lbforaging:Foraging-8x8-2p-3f-v3", "env.time_limit=25"])
         with warnings.catch_warnings():
             warnings.simplefilter("error")
