@@ -7,6 +7,7 @@
 #include "retms.cuh"
 #include "qmix.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -162,8 +163,8 @@ struct marl_dqn {
   // cfg.standardise_returns: RunningMeanStd over the TD targets (mean[n] | var[n], count, partial sums, returns / chosen-Q scratch)
   int standardise = 0, n_stat = 0; float *ret_ms = nullptr, *ret = nullptr, *chosen = nullptr; double *ret_count = nullptr, *ret_part = nullptr;
   // QMIX (hp.mixer == 2): the mixing network's parameters / Adam state / gradient (+ 4 statistics), per-sample records, chunked partial sums, tile list
-  QmixLayout ql = {}; float *mix = nullptr, *mix_tgt = nullptr, *mix_m = nullptr, *mix_v = nullptr, *mix_grad = nullptr, *mix_rec = nullptr, *mix_part = nullptr;
-  QmixTile* mix_tiles = nullptr; int mix_n_tiles = 0;
+  QmixLayout ql = {}; float *mix = nullptr, *mix_tgt = nullptr, *mix_m = nullptr, *mix_v = nullptr, *mix_grad = nullptr, *mix_rec = nullptr, *mix_part = nullptr, *mix_img = nullptr, *mix_img_tgt = nullptr;
+  QmixTile* mix_tiles = nullptr; int mix_n_tiles = 0; QmixMicro* mix_micro = nullptr; int mix_n_micro = 0; bool mix_wgrad_tiles = false;
 };
 static const int kTimingPairs = 1024;
 
@@ -219,7 +220,7 @@ int marl_dqn_destroy(marl_dqn* h) {
   cudaFree(h->theta); cudaFree(h->theta_tgt); cudaFree(h->m); cudaFree(h->v); cudaFree(h->grad); cudaFree(h->scratch);
   cudaFree(h->loss_part); cudaFree(h->tq); cudaFree(h->q_all); cudaFree(h->td); cudaFree(h->loss_dev); cudaFree(h->sumsq); cudaFree(h->idx); cudaFree(h->image); cudaFree(h->image_tgt); cudaFree(h->image_bwd); cudaFree(h->tc_h1); cudaFree(h->tc_h2); cudaFree(h->tc_dh1); cudaFree(h->tc_rec); cudaFree(h->tc_x); cudaFree(h->grid_barrier);
   for (int r = 0; r < kMaxRanks; ++r) if (h->peer_base[r] != nullptr && r != h->xchg.rank) cudaIpcCloseMemHandle(h->peer_base[r]);
-  cudaFree(h->mix); cudaFree(h->mix_tgt); cudaFree(h->mix_m); cudaFree(h->mix_v); cudaFree(h->mix_grad); cudaFree(h->mix_rec); cudaFree(h->mix_part); cudaFree(h->mix_tiles);
+  cudaFree(h->mix); cudaFree(h->mix_tgt); cudaFree(h->mix_m); cudaFree(h->mix_v); cudaFree(h->mix_grad); cudaFree(h->mix_rec); cudaFree(h->mix_part); cudaFree(h->mix_tiles); cudaFree(h->mix_micro); cudaFree(h->mix_img); cudaFree(h->mix_img_tgt);
   cudaFree(h->xbuf); cudaFree(h->ret_ms); cudaFree(h->ret); cudaFree(h->chosen); cudaFree(h->ret_count); cudaFree(h->ret_part);
   for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
@@ -269,24 +270,35 @@ int marl_dqn_qmix_init(marl_dqn* h, int32_t embed_dim, int32_t hypernet_layers, 
   MARL_REQUIRE(embed_dim >= 4 && embed_dim <= kQmixEmbedMax && embed_dim % 4 == 0, "marl_dqn_qmix_init: embed_dim %d not supported (multiple of 4, <= %d)", embed_dim, kQmixEmbedMax);
   MARL_REQUIRE(hypernet_embed >= 4 && hypernet_embed <= kQmixHypMax && hypernet_embed % 4 == 0, "marl_dqn_qmix_init: hypernet_embed %d not supported (multiple of 4, <= %d)", hypernet_embed, kQmixHypMax);
   const int N = h->ns.n_agents, S = N * h->ns.in;
-  MARL_REQUIRE(S <= kQmixStateMax && N * embed_dim <= kQmixNEMax, "marl_dqn_qmix_init: state_dim %d (<= %d) or n_agents x embed_dim %d (<= %d) too large", S, kQmixStateMax, N * embed_dim, kQmixNEMax);
+  MARL_REQUIRE(S <= kQmixStateMax && N <= kQmixAgentsMax, "marl_dqn_qmix_init: state_dim %d (<= %d) or n_agents %d (<= %d) too large", S, kQmixStateMax, N, kQmixAgentsMax);
   MARL_CUDA_TRY(cudaSetDevice(h->device));
   h->ql = qmix_layout(N, S, embed_dim, hypernet_embed);
   const size_t n = (size_t)h->ql.n, samples = (size_t)h->max_batch * h->max_T;
-  MARL_REQUIRE(n * sizeof(float) <= 200 * 1024, "marl_dqn_qmix_init: the mixer's %zu parameters do not fit shared memory", n);
+  MARL_REQUIRE(qm_smem_bytes(h->ql) <= 227 * 1024, "marl_dqn_qmix_init: the mixer's %zu parameters + a 32-sample tile (%zu bytes) do not fit shared memory", n, qm_smem_bytes(h->ql));
   std::vector<QmixTile> tiles(kQmixMaxTiles);
   const int nt = qmix_tiles(h->ql, tiles.data());
   MARL_REQUIRE(nt > 0, "marl_dqn_qmix_init: too many weight-gradient tiles");
   int rc = 0;
   rc |= dqn_alloc(&h->mix, n); rc |= dqn_alloc(&h->mix_tgt, n); rc |= dqn_alloc(&h->mix_m, n); rc |= dqn_alloc(&h->mix_v, n); rc |= dqn_alloc(&h->mix_grad, n + 4);
-  rc |= dqn_alloc(&h->mix_rec, (size_t)h->ql.R * samples); rc |= dqn_alloc(&h->mix_part, (size_t)kQmixChunks * n);
+  rc |= dqn_alloc(&h->mix_rec, (size_t)h->ql.R * samples); rc |= dqn_alloc(&h->mix_part, (size_t)(2 * h->n_sm > kQmixChunks ? 2 * h->n_sm : kQmixChunks) * n);
   rc |= dqn_alloc(reinterpret_cast<float**>(&h->mix_tiles), (size_t)nt * sizeof(QmixTile) / 4);
-  cudaFree(h->loss_part); h->loss_part = nullptr;   // one block of statistics per kQmixThreads samples
-  rc |= dqn_alloc(&h->loss_part, 4 * ((size_t)h->n_sm + samples / kQmixThreads + 2));
+  rc |= dqn_alloc(&h->mix_img, (n + 3) & ~(size_t)3); rc |= dqn_alloc(&h->mix_img_tgt, (n + 3) & ~(size_t)3);
+  cudaFree(h->loss_part); h->loss_part = nullptr;   // one block of statistics per tile of kQmTS samples
+  rc |= dqn_alloc(&h->loss_part, 4 * ((size_t)h->n_sm + samples / kQmTS + 2));
   if (rc) return MARL_ENOMEM;
   MARL_CUDA_TRY(cudaMemcpy(h->mix_tiles, tiles.data(), (size_t)nt * sizeof(QmixTile), cudaMemcpyHostToDevice));
   h->mix_n_tiles = nt;
-  MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * sizeof(float))));
+  std::vector<QmixMicro> micro(1 << 14);
+  const int nm = qmix_micro_tiles(h->ql, micro.data(), (int)micro.size());
+  MARL_REQUIRE(nm > 0, "marl_dqn_qmix_init: too many weight-gradient micro-tiles");
+  if (dqn_alloc(reinterpret_cast<float**>(&h->mix_micro), (size_t)nm * sizeof(QmixMicro) / 4)) return MARL_ENOMEM;
+  MARL_CUDA_TRY(cudaMemcpy(h->mix_micro, micro.data(), (size_t)nm * sizeof(QmixMicro), cudaMemcpyHostToDevice));
+  h->mix_n_micro = nm;
+  const size_t wg_smem = (size_t)(h->ql.R + 2) * kQmP * sizeof(float);
+  const char* ev = getenv("MARL_QMIX_WGRAD_TILES");
+  h->mix_wgrad_tiles = (ev != nullptr && ev[0] == '1') || wg_smem > 110 * 1024;   // the single-read form needs all record fields of 32 samples in shared memory
+  if (!h->mix_wgrad_tiles) MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
+  MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qm_smem_bytes(h->ql)));
   return MARL_OK;
 }
 int marl_dqn_qmix_ptrs(marl_dqn* h, float** mix, float** mix_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params) {
@@ -396,10 +408,17 @@ static int dqn_grads(marl_dqn* h, const marl_traj_view* traj, const int32_t* epi
     qp.L = h->ql; qp.q = h->q_all; qp.tq = h->tq; qp.traj = src.traj; qp.idx = episode_idx; qp.B = batch; qp.A = h->ns.out; qp.D = h->ns.in;
     qp.gamma = h->hp.gamma; qp.double_q = h->hp.double_q; qp.mix = h->mix; qp.mix_tgt = h->mix_tgt; qp.rec = h->mix_rec; qp.td = h->td;
     qp.loss_part = h->loss_part + 4 * (size_t)n_loss_parts;
-    const int Sn = batch * T, qb = (Sn + kQmixThreads - 1) / kQmixThreads, n = h->ql.n;
-    qmix_mix_kernel<<<qb, kQmixThreads, (size_t)n * sizeof(float), st>>>(qp);
-    const int chunk_len = (((Sn + kQmixChunks - 1) / kQmixChunks) + 31) & ~31, chunks = (Sn + chunk_len - 1) / chunk_len;
-    qmix_wgrad_kernel<<<dim3(h->mix_n_tiles, chunks), 256, 0, st>>>(h->mix_rec, Sn, h->mix_tiles, chunk_len, h->mix_part, n);
+    const int Sn = batch * T, qb = (Sn + kQmTS - 1) / kQmTS, n = h->ql.n;
+    qmix_pack_kernel<<<dim3((n + 255) / 256, 2), 256, 0, st>>>(h->ql, h->mix, h->mix_tgt, h->mix_img, h->mix_img_tgt);
+    qmix_mix_kernel<<<qb, kQmWarps * 32, qm_smem_bytes(h->ql), st>>>(qp, h->mix_img, h->mix_img_tgt);
+    const int want = h->mix_wgrad_tiles ? kQmixChunks : 2 * h->n_sm;
+    const int chunk_len = (((Sn + want - 1) / want) + 31) & ~31, chunks = (Sn + chunk_len - 1) / chunk_len;
+    if (h->mix_wgrad_tiles) {
+      qmix_wgrad_kernel<<<dim3(h->mix_n_tiles, chunks), 256, 0, st>>>(h->mix_rec, Sn, h->mix_tiles, chunk_len, h->mix_part, n);
+    } else {
+      for (int round = 0; round * kQmMicroPerRound < h->mix_n_micro; ++round)
+        qmix_wgrad2_kernel<<<chunks, 256, (size_t)(h->ql.R + 2) * kQmP * sizeof(float), st>>>(h->mix_rec, Sn, h->ql.R, h->mix_micro, h->mix_n_micro, round, chunk_len, h->mix_part, n);
+    }
     qmix_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->mix_part, chunks, n, h->mix_grad, qp.loss_part, qb);
     MARL_CUDA_TRY(cudaGetLastError());
     n_loss_parts += qb;

@@ -5,13 +5,15 @@
 //
 // The agents' networks stay on the tensor-core training pass: the mixer only replaces VDN's sum, i.e. it turns the agents' Q-values of every sampled
 // (episode, step) into a TD error and hands dL/dq_a back through td_ext (per agent).  Work split:
-//   qmix_mix_kernel    one thread per (episode b, step t).  Target: double-Q pick per agent at t + 1, target mixer on the state at t + 1.  Online:
-//                      mixer on the state at t, delta = Q_tot - (r + gamma (1 - done) Q_tot_target), dL/dq_a -> td[a][b][t], and the back-propagated
-//                      values at the OUTPUT of each of the mixer's seven linear layers next to those layers' inputs -> a per-sample record,
-//                      stored field-major ([field][sample]: coalesced for this kernel's writes and the next kernel's reads).
-//                      The mixer's parameters sit in shared memory (49 KB at N = 2, S = 30); all lanes read the same weight (broadcast).
-//   qmix_wgrad_kernel  dW = sum over samples of (output gradient) x (input): 32 x 32 tiles of every layer's [O][I + 1 (bias)] matrix, the samples in
-//                      kQmixChunks chunks -> partial sums (every parameter belongs to exactly one tile).
+//   qmix_pack_kernel   the online and the target mixer's weights, transposed per layer ([I][O]) -> two images (12 k floats each at N = 2, S = 30).
+//   qmix_mix_kernel    a tile of 32 (episode b, step t) samples per CTA, lane = sample, the 8 warps share each layer's outputs; image and the tile's
+//                      activations in shared memory (107 KB: two CTAs per SM).  Target: double-Q pick per agent at t + 1, target mixer on the state
+//                      at t + 1.  Online: mixer on the state at t, delta = Q_tot - (r + gamma (1 - done) Q_tot_target), dL/dq_a -> td[a][b][t], and the
+//                      back-propagated values at the OUTPUT of each of the mixer's seven linear layers next to those layers' inputs -> a per-sample
+//                      record, stored field-major ([field][sample]: coalesced for this kernel's writes and the next kernel's reads).
+//   qmix_wgrad2_kernel dW = sum over samples of (output gradient) x (input) for every layer's [O][I + 1 (bias)] matrix: one CTA per run of samples, the
+//                      record read once, 4 x 8 register micro-tiles -> per-CTA partial sums (every parameter belongs to exactly one micro-tile).
+//                      (qmix_wgrad_kernel: the first, tile-per-CTA form, kept behind MARL_QMIX_WGRAD_TILES=1 as a cross-check.)
 //   qmix_reduce_kernel the chunks in fixed order -> gradient; the filled count next to it (Adam's 1 / filled.sum()).
 // The mixer's parameters take the shared Adam step WITHOUT gradient clipping: the reference clips self.critic.parameters() only (dqn/model.py:169-170).
 #pragma once
@@ -19,7 +21,7 @@
 
 namespace marl {
 
-constexpr int kQmixThreads = 128, kQmixEmbedMax = 64, kQmixHypMax = 64, kQmixNEMax = 512, kQmixStateMax = 256, kQmixChunks = 32, kQmixMaxTiles = 512;
+constexpr int kQmixEmbedMax = 64, kQmixHypMax = 64, kQmixAgentsMax = 8, kQmixStateMax = 256, kQmixChunks = 32, kQmixMaxTiles = 512;
 
 struct QmixLayout {   // offsets (floats) into the mixer's flat parameter vector (reference state_dict order) and into a sample's record
   int N, S, E, He, n;
@@ -53,158 +55,227 @@ struct QmixParams {
   float* loss_part;   // [gridDim][4]
 };
 
-// rows of `w` ([O][I], I arbitrary) times the thread's x[I]: four outputs per pass so that a load of x feeds four FMAs
-__device__ __forceinline__ void qmix_rows_x(const float* __restrict__ w, const float* __restrict__ bias, const float* x, int O, int I, float* out, bool relu) {
-  for (int o = 0; o < O; o += 4) {
-    float a0 = bias[o], a1 = bias[o + 1], a2 = bias[o + 2], a3 = bias[o + 3];
-    const float* w0 = w + (size_t)o * I;
-    for (int i = 0; i < I; ++i) {
-      const float xv = x[i];
-      a0 = fmaf(w0[i], xv, a0); a1 = fmaf(w0[I + i], xv, a1); a2 = fmaf(w0[2 * I + i], xv, a2); a3 = fmaf(w0[3 * I + i], xv, a3);
-    }
-    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-    out[o] = a0; out[o + 1] = a1; out[o + 2] = a2; out[o + 3] = a3;
+// ---- qmix_mix_kernel: 32 samples per CTA (lane = sample), 8 warps share each layer's outputs -----------------------------------------------------
+// Shared memory: the mixer's image (weights TRANSPOSED, [I][O], so that a thread's four consecutive outputs are one 16-byte broadcast load and the
+// transposed products of the backward read rows) + the tile's activations, field-major with a 33-float pitch (lane = sample: conflict-free).
+constexpr int kQmTS = 32, kQmP = 33, kQmWarps = 8;
+
+// image: same offsets as QmixLayout, every weight block transposed ([I][O]); built once per update by qmix_pack_kernel for the online and target mixer
+__global__ void __launch_bounds__(256) qmix_pack_kernel(QmixLayout L, const float* __restrict__ mix, const float* __restrict__ mix_tgt, float* img, float* img_tgt) {
+  const float* src = blockIdx.y ? mix_tgt : mix;
+  float* dst = blockIdx.y ? img_tgt : img;
+  const int woff[7] = {L.w1a, L.w1b, L.wfa, L.wfb, L.wb, L.wva, L.wvb}, O[7] = {L.He, L.N * L.E, L.He, L.E, L.E, L.E, 1}, I[7] = {L.S, L.He, L.S, L.He, L.S, L.S, L.E};
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < L.n; j += gridDim.x * 256) {
+    int k = 6;
+    while (k > 0 && j < woff[k]) --k;
+    const int r = j - woff[k];
+    if (r < O[k] * I[k]) { const int o = r / I[k], i = r - o * I[k]; dst[woff[k] + i * O[k] + o] = src[j]; }
+    else dst[j] = src[j];   // bias
   }
 }
-// the same with I a multiple of 4 and 16-byte aligned rows (the hypernetworks' second layers)
-__device__ __forceinline__ void qmix_rows_h(const float* __restrict__ w, const float* __restrict__ bias, const float* h, int O, int I, float* out) {
-  for (int o = 0; o < O; o += 4) {
-    float a0 = bias[o], a1 = bias[o + 1], a2 = bias[o + 2], a3 = bias[o + 3];
-    const float4* w0 = reinterpret_cast<const float4*>(w + (size_t)o * I);
-    const int I4 = I >> 2;
-    for (int i = 0; i < I4; ++i) {
-      const float h0 = h[4 * i], h1 = h[4 * i + 1], h2 = h[4 * i + 2], h3 = h[4 * i + 3];
-      const float4 u0 = w0[i], u1 = w0[I4 + i], u2 = w0[2 * I4 + i], u3 = w0[3 * I4 + i];
-      a0 = fmaf(u0.x, h0, a0); a0 = fmaf(u0.y, h1, a0); a0 = fmaf(u0.z, h2, a0); a0 = fmaf(u0.w, h3, a0);
-      a1 = fmaf(u1.x, h0, a1); a1 = fmaf(u1.y, h1, a1); a1 = fmaf(u1.z, h2, a1); a1 = fmaf(u1.w, h3, a1);
-      a2 = fmaf(u2.x, h0, a2); a2 = fmaf(u2.y, h1, a2); a2 = fmaf(u2.z, h2, a2); a2 = fmaf(u2.w, h3, a2);
-      a3 = fmaf(u3.x, h0, a3); a3 = fmaf(u3.y, h1, a3); a3 = fmaf(u3.z, h2, a3); a3 = fmaf(u3.w, h3, a3);
+
+struct QmSmem { float *W, *X, *H1, *H2, *HV, *PRE, *RAWF, *RAW1, *QA, *RED, *RED2; };
+__host__ __device__ inline int qm_act_rows(const QmixLayout& L) { return L.S + 2 * L.He + 3 * L.E + L.N * L.E + L.N + kQmWarps + L.N * kQmWarps; }
+__host__ __device__ inline size_t qm_smem_bytes(const QmixLayout& L) { return ((size_t)((L.n + 3) & ~3) + (size_t)qm_act_rows(L) * kQmP) * sizeof(float); }
+
+// out[o][lane] = act(bias[o] + sum_i wT[i][o] in[i][lane]) for this warp's groups of 4 G consecutive outputs: one load of the input feeds 4 G FMAs,
+// a weight load (16 bytes, the same address in every lane) four.  G = 2 whenever the layer is wide enough to keep all eight warps busy.
+template <int G>
+__device__ __forceinline__ void qm_layer_g(const float* __restrict__ wT, const float* __restrict__ bias, const float* in, float* out, int I, int O, bool relu, int warp, int lane) {
+  for (int o0 = 4 * G * warp; o0 < O; o0 += 4 * G * kQmWarps) {
+    float a[4 * G];
+#pragma unroll
+    for (int k = 0; k < 4 * G; ++k) a[k] = bias[o0 + k];
+    const float* wp = wT + o0;
+    const float* xp = in + lane;
+#pragma unroll 4
+    for (int i = 0; i < I; ++i, wp += O, xp += kQmP) {
+      const float xv = *xp;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 w = *reinterpret_cast<const float4*>(wp + 4 * g);
+        a[4 * g] = fmaf(w.x, xv, a[4 * g]); a[4 * g + 1] = fmaf(w.y, xv, a[4 * g + 1]); a[4 * g + 2] = fmaf(w.z, xv, a[4 * g + 2]); a[4 * g + 3] = fmaf(w.w, xv, a[4 * g + 3]);
+      }
     }
-    out[o] = a0; out[o + 1] = a1; out[o + 2] = a2; out[o + 3] = a3;
+    float* op = out + o0 * kQmP + lane;
+#pragma unroll
+    for (int k = 0; k < 4 * G; ++k) op[k * kQmP] = relu ? fmaxf(a[k], 0.f) : a[k];
   }
 }
-// dh[I] = sum_o d[o] w[o][I] (transposed product), I a multiple of 4; then the ReLU mask of the layer below (h > 0)
-__device__ __forceinline__ void qmix_rows_t(const float* __restrict__ w, const float* d, int O, int I, const float* h, float* out) {
-  for (int i = 0; i < I; i += 4) {
+__device__ __forceinline__ void qm_layer(const float* __restrict__ wT, const float* __restrict__ bias, const float* in, float* out, int I, int O, bool relu, int warp, int lane) {
+  if ((O & 63) == 0) qm_layer_g<2>(wT, bias, in, out, I, O, relu, warp, lane);
+  else qm_layer_g<1>(wT, bias, in, out, I, O, relu, warp, lane);
+}
+// rec[r_off + j][s] = (h[j][lane] > 0) sum_o d[o][lane] wT[j][o]: the gradient at a hypernetwork's hidden pre-activation (O a multiple of 4)
+__device__ __forceinline__ void qm_layer_t(const float* __restrict__ wT, const float* d, const float* h, int I, int O, float* rec_col, int Sn, bool live, int warp, int lane) {
+  for (int j0 = 4 * warp; j0 < I; j0 += 4 * kQmWarps) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int o = 0; o < O; ++o) {
-      const float dv = d[o];
-      const float4 u = *reinterpret_cast<const float4*>(w + (size_t)o * I + i);
-      a0 = fmaf(u.x, dv, a0); a1 = fmaf(u.y, dv, a1); a2 = fmaf(u.z, dv, a2); a3 = fmaf(u.w, dv, a3);
+    const float* w = wT + j0 * O;
+#pragma unroll 2
+    for (int o = 0; o < O; o += 4) {
+      const float d0 = d[o * kQmP + lane], d1 = d[(o + 1) * kQmP + lane], d2 = d[(o + 2) * kQmP + lane], d3 = d[(o + 3) * kQmP + lane];
+      const float4 u0 = *reinterpret_cast<const float4*>(w + o), u1 = *reinterpret_cast<const float4*>(w + O + o);
+      const float4 u2 = *reinterpret_cast<const float4*>(w + 2 * O + o), u3 = *reinterpret_cast<const float4*>(w + 3 * O + o);
+      a0 = fmaf(u0.x, d0, a0); a0 = fmaf(u0.y, d1, a0); a0 = fmaf(u0.z, d2, a0); a0 = fmaf(u0.w, d3, a0);
+      a1 = fmaf(u1.x, d0, a1); a1 = fmaf(u1.y, d1, a1); a1 = fmaf(u1.z, d2, a1); a1 = fmaf(u1.w, d3, a1);
+      a2 = fmaf(u2.x, d0, a2); a2 = fmaf(u2.y, d1, a2); a2 = fmaf(u2.z, d2, a2); a2 = fmaf(u2.w, d3, a2);
+      a3 = fmaf(u3.x, d0, a3); a3 = fmaf(u3.y, d1, a3); a3 = fmaf(u3.z, d2, a3); a3 = fmaf(u3.w, d3, a3);
     }
-    out[i] = h[i] > 0.f ? a0 : 0.f; out[i + 1] = h[i + 1] > 0.f ? a1 : 0.f; out[i + 2] = h[i + 2] > 0.f ? a2 : 0.f; out[i + 3] = h[i + 3] > 0.f ? a3 : 0.f;
+    if (live) {
+      rec_col[(size_t)j0 * Sn] = h[j0 * kQmP + lane] > 0.f ? a0 : 0.f; rec_col[(size_t)(j0 + 1) * Sn] = h[(j0 + 1) * kQmP + lane] > 0.f ? a1 : 0.f;
+      rec_col[(size_t)(j0 + 2) * Sn] = h[(j0 + 2) * kQmP + lane] > 0.f ? a2 : 0.f; rec_col[(size_t)(j0 + 3) * Sn] = h[(j0 + 3) * kQmP + lane] > 0.f ? a3 : 0.f;
+    }
   }
 }
 
 __device__ __forceinline__ float qmix_sgn(float x) { return (float)(x > 0.f) - (float)(x < 0.f); }   // torch.abs' gradient (0 at 0)
 
-// Mixer forward of one sample with the parameters `w` (shared memory).  Leaves h1, h2, hv, raw1 (W1 before abs), rawf, pre (before elu) for the backward.
-__device__ __forceinline__ float qmix_forward(const float* __restrict__ w, const QmixLayout& L, const float* x, const float* qa,
-                                              float* h1, float* h2, float* hv, float* raw1, float* rawf, float* pre) {
-  qmix_rows_x(w + L.w1a, w + L.b1a, x, L.He, L.S, h1, true);
-  qmix_rows_x(w + L.wfa, w + L.bfa, x, L.He, L.S, h2, true);
-  qmix_rows_x(w + L.wva, w + L.bva, x, L.E, L.S, hv, true);
-  qmix_rows_x(w + L.wb, w + L.bb, x, L.E, L.S, pre, false);
-  qmix_rows_h(w + L.w1b, w + L.b1b, h1, L.N * L.E, L.He, raw1);
-  qmix_rows_h(w + L.wfb, w + L.bfb, h2, L.E, L.He, rawf);
-  float y = w[L.bvb];
-  for (int e = 0; e < L.E; ++e) {
-    float p = pre[e];
-    for (int a = 0; a < L.N; ++a) p = fmaf(qa[a], fabsf(raw1[a * L.E + e]), p);
-    pre[e] = p;
-    const float hid = p > 0.f ? p : expm1f(p);
-    y = fmaf(hid, fabsf(rawf[e]), y);
-    y = fmaf(w[L.wvb + e], hv[e], y);
+// Forward of the tile with the image in sm.W: the four state-fed layers, the hypernetworks' second layers, then Q_tot per sample.  On return
+// PRE holds the ELU's argument and every thread of lane `lane` holds that sample's Q_tot.
+__device__ __forceinline__ float qm_forward(const QmSmem& sm, const QmixLayout& L, int warp, int lane) {
+  const float* W = sm.W;
+  qm_layer(W + L.w1a, W + L.b1a, sm.X, sm.H1, L.S, L.He, true, warp, lane);
+  qm_layer(W + L.wfa, W + L.bfa, sm.X, sm.H2, L.S, L.He, true, warp, lane);
+  qm_layer(W + L.wva, W + L.bva, sm.X, sm.HV, L.S, L.E, true, warp, lane);
+  qm_layer(W + L.wb, W + L.bb, sm.X, sm.PRE, L.S, L.E, false, warp, lane);
+  __syncthreads();
+  qm_layer(W + L.w1b, W + L.b1b, sm.H1, sm.RAW1, L.He, L.N * L.E, false, warp, lane);
+  qm_layer(W + L.wfb, W + L.bfb, sm.H2, sm.RAWF, L.He, L.E, false, warp, lane);
+  __syncthreads();
+  float part = 0.f;
+  for (int e = warp; e < L.E; e += kQmWarps) {
+    float pe = sm.PRE[e * kQmP + lane];
+    for (int a = 0; a < L.N; ++a) pe = fmaf(sm.QA[a * kQmP + lane], fabsf(sm.RAW1[(a * L.E + e) * kQmP + lane]), pe);
+    sm.PRE[e * kQmP + lane] = pe;
+    const float hid = pe > 0.f ? pe : expm1f(pe);
+    part = fmaf(hid, fabsf(sm.RAWF[e * kQmP + lane]), part);
+    part = fmaf(W[L.wvb + e], sm.HV[e * kQmP + lane], part);
   }
+  sm.RED[warp * kQmP + lane] = part;
+  __syncthreads();
+  float y = W[L.bvb];
+#pragma unroll
+  for (int k = 0; k < kQmWarps; ++k) y += sm.RED[k * kQmP + lane];
   return y;
 }
 
-__global__ void __launch_bounds__(kQmixThreads) qmix_mix_kernel(QmixParams p) {
-  extern __shared__ __align__(16) float qw[];
-  __shared__ float red[2 * kQmixThreads];
+// the tile's inputs: state = the agents' observations at step t + dt side by side; q_a = chosen Q (dt = 0) or the double-Q / max target pick (dt = 1)
+__device__ __forceinline__ void qm_load_inputs(const QmSmem& sm, const QmixParams& p, int s0, int Sn, int dt) {
   const QmixLayout& L = p.L;
-  const int T = p.traj.T, Sn = p.B * T, s = blockIdx.x * kQmixThreads + threadIdx.x;
+  const int T = p.traj.T;
+  for (int k = threadIdx.x; k < kQmTS * L.S; k += kQmWarps * 32) {
+    const int sl = k / L.S, i = k - sl * L.S, s = s0 + sl;
+    float v = 0.f;
+    if (s < Sn) {
+      const int b = s / T, t = s - b * T, a = i / p.D, d = i - a * p.D;
+      v = p.traj.obs[(((size_t)p.idx[b] * L.N + a) * (T + 1) + t + dt) * p.D + d];
+    }
+    sm.X[i * kQmP + sl] = v;
+  }
+  for (int k = threadIdx.x; k < kQmTS * L.N; k += kQmWarps * 32) {
+    const int a = k / kQmTS, sl = k - a * kQmTS, s = s0 + sl;
+    float v = 0.f;
+    if (s < Sn) {
+      const int b = s / T, t = s - b * T;
+      const size_t row = ((size_t)a * p.B + b) * (T + 1) + t + dt;
+      const float* q1 = p.q + row * p.A;
+      if (dt == 0) {
+        v = q1[p.traj.act[((size_t)p.idx[b] * L.N + a) * T + t]];
+      } else {
+        const float* t1 = p.tq + row * p.A;
+        if (p.double_q) {
+          int best = 0; float bv = q1[0];
+          for (int o = 1; o < p.A; ++o) if (q1[o] > bv) { bv = q1[o]; best = o; }
+          v = t1[best];
+        } else {
+          v = t1[0];
+          for (int o = 1; o < p.A; ++o) v = fmaxf(v, t1[o]);
+        }
+      }
+    }
+    sm.QA[a * kQmP + sl] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kQmWarps * 32, 2) qmix_mix_kernel(QmixParams p, const float* __restrict__ img, const float* __restrict__ img_tgt) {
+  extern __shared__ __align__(16) float qsm[];
+  const QmixLayout& L = p.L;
+  QmSmem sm;
+  sm.W = qsm;
+  float* o = qsm + ((L.n + 3) & ~3);
+  sm.X = o; o += L.S * kQmP; sm.H1 = o; o += L.He * kQmP; sm.H2 = o; o += L.He * kQmP; sm.HV = o; o += L.E * kQmP; sm.PRE = o; o += L.E * kQmP;
+  sm.RAWF = o; o += L.E * kQmP; sm.RAW1 = o; o += L.N * L.E * kQmP; sm.QA = o; o += L.N * kQmP; sm.RED = o; o += kQmWarps * kQmP; sm.RED2 = o;
+  const int T = p.traj.T, Sn = p.B * T, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = blockIdx.x * kQmTS, s = s0 + lane;
   const bool live = s < Sn;
   const int b = live ? s / T : 0, t = live ? s - b * T : 0;
   const size_t ep = (size_t)p.idx[b];
-  float x[kQmixStateMax], qa[MARL_MAX_AGENTS], h1[kQmixHypMax], h2[kQmixHypMax], hv[kQmixEmbedMax], pre[kQmixEmbedMax], rawf[kQmixEmbedMax], raw1[kQmixNEMax];
-  // ---- target: r + gamma (1 - done) Q_tot'(double-Q picks at t + 1, state at t + 1) ----
-  for (int i = threadIdx.x; i < L.n; i += kQmixThreads) qw[i] = p.mix_tgt[i];
+  const int n4 = (L.n + 3) >> 2;
+  // ---- target: Q_tot' of the picks at t + 1 on the state at t + 1 ----
+  for (int i = threadIdx.x; i < n4; i += kQmWarps * 32) reinterpret_cast<float4*>(sm.W)[i] = reinterpret_cast<const float4*>(img_tgt)[i];
+  qm_load_inputs(sm, p, s0, Sn, 1);
   __syncthreads();
-  float ytgt = 0.f;
+  const float ytgt = qm_forward(sm, L, warp, lane);
+  __syncthreads();
+  // ---- online ----
+  for (int i = threadIdx.x; i < n4; i += kQmWarps * 32) reinterpret_cast<float4*>(sm.W)[i] = reinterpret_cast<const float4*>(img)[i];
+  qm_load_inputs(sm, p, s0, Sn, 0);
+  __syncthreads();
+  const float y = qm_forward(sm, L, warp, lane);
+  const float filled = live ? (float)p.traj.filled[ep * T + t] : 0.f;
+  const float ret = live ? p.traj.rew[(ep * L.N + 0) * T + t] + p.gamma * ytgt * (1.f - (float)p.traj.done[ep * (T + 1) + t + 1]) : 0.f;
+  const float delta = live ? y - ret : 0.f, dy = 2.f * delta * filled;
+  float* rc = p.rec + s;   // this sample's column of the field-major record
   if (live) {
-    for (int a = 0; a < L.N; ++a) {
-      const size_t row = ((size_t)a * p.B + b) * (T + 1) + t + 1;
-      const float* q1 = p.q + row * p.A; const float* t1 = p.tq + row * p.A;
-      if (p.double_q) {
-        int best = 0; float bv = q1[0];
-        for (int o = 1; o < p.A; ++o) if (q1[o] > bv) { bv = q1[o]; best = o; }
-        qa[a] = t1[best];
-      } else {
-        float m = t1[0];
-        for (int o = 1; o < p.A; ++o) m = fmaxf(m, t1[o]);
-        qa[a] = m;
-      }
-      const float* ob = p.traj.obs + ((ep * L.N + a) * (T + 1) + t + 1) * p.D;
-      for (int d = 0; d < p.D; ++d) x[a * p.D + d] = ob[d];
-    }
-    ytgt = qmix_forward(qw, L, x, qa, h1, h2, hv, raw1, rawf, pre);
+    // the layers' inputs (x, h1, h2) -> record; rows are shared out over the warps
+    for (int i = warp; i < L.S; i += kQmWarps) rc[(size_t)(L.r_x + i) * Sn] = sm.X[i * kQmP + lane];
+    for (int j = warp; j < L.He; j += kQmWarps) { rc[(size_t)(L.r_h1 + j) * Sn] = sm.H1[j * kQmP + lane]; rc[(size_t)(L.r_h2 + j) * Sn] = sm.H2[j * kQmP + lane]; }
+    if (warp == 0) rc[(size_t)L.r_dv * Sn] = dy;
   }
-  __syncthreads();
-  // ---- online: Q_tot of the chosen actions, TD error, gradients at every linear layer's output ----
-  for (int i = threadIdx.x; i < L.n; i += kQmixThreads) qw[i] = p.mix[i];
-  __syncthreads();
-  float loss = 0.f, fill = 0.f;
-  if (live) {
-    for (int a = 0; a < L.N; ++a) {
-      const size_t row = ((size_t)a * p.B + b) * (T + 1) + t;
-      qa[a] = p.q[row * p.A + p.traj.act[(ep * L.N + a) * T + t]];
-      const float* ob = p.traj.obs + ((ep * L.N + a) * (T + 1) + t) * p.D;
-      for (int d = 0; d < p.D; ++d) x[a * p.D + d] = ob[d];
-    }
-    const float y = qmix_forward(qw, L, x, qa, h1, h2, hv, raw1, rawf, pre);
-    const float filled = (float)p.traj.filled[ep * T + t];
-    const float ret = p.traj.rew[(ep * L.N + 0) * T + t] + p.gamma * ytgt * (1.f - (float)p.traj.done[ep * (T + 1) + t + 1]);
-    const float delta = y - ret, dy = 2.f * delta * filled;
-    loss = delta * delta * filled; fill = filled;
-    float* rc = p.rec + s;
-    for (int i = 0; i < L.S; ++i) rc[(size_t)(L.r_x + i) * Sn] = x[i];
-    for (int j = 0; j < L.He; ++j) { rc[(size_t)(L.r_h1 + j) * Sn] = h1[j]; rc[(size_t)(L.r_h2 + j) * Sn] = h2[j]; }
-    rc[(size_t)L.r_dv * Sn] = dy;
-    // per embedding unit: V's hidden layer, w_final, the ELU; dpre overwrites pre, d_rawf overwrites rawf
-    for (int e = 0; e < L.E; ++e) {
-      const float pe = pre[e], hid = pe > 0.f ? pe : expm1f(pe), rf = rawf[e];
-      const float dp = dy * fabsf(rf) * (pe > 0.f ? 1.f : hid + 1.f);
-      const float drf = dy * hid * qmix_sgn(rf);
-      rc[(size_t)(L.r_hv + e) * Sn] = hv[e];
-      rc[(size_t)(L.r_dzv + e) * Sn] = hv[e] > 0.f ? dy * qw[L.wvb + e] : 0.f;
+  // per embedding unit: V's hidden layer, w_final, the ELU; PRE <- dL/d(ELU argument), RAWF <- dL/d(w_final before abs), RAW1 <- dL/d(W1 before abs)
+  float dq[MARL_MAX_AGENTS > 8 ? 8 : MARL_MAX_AGENTS];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) dq[a] = 0.f;
+  for (int e = warp; e < L.E; e += kQmWarps) {
+    const float pe = sm.PRE[e * kQmP + lane], hid = pe > 0.f ? pe : expm1f(pe), rf = sm.RAWF[e * kQmP + lane], hv = sm.HV[e * kQmP + lane];
+    const float dp = dy * fabsf(rf) * (pe > 0.f ? 1.f : hid + 1.f);
+    const float drf = dy * hid * qmix_sgn(rf);
+    if (live) {
+      rc[(size_t)(L.r_hv + e) * Sn] = hv;
+      rc[(size_t)(L.r_dzv + e) * Sn] = hv > 0.f ? dy * sm.W[L.wvb + e] : 0.f;
       rc[(size_t)(L.r_drawf + e) * Sn] = drf;
       rc[(size_t)(L.r_dhb + e) * Sn] = dp;
-      pre[e] = dp; rawf[e] = drf;
     }
-    for (int a = 0; a < L.N; ++a) {
-      float dq = 0.f;
-      for (int e = 0; e < L.E; ++e) {
-        const float r1 = raw1[a * L.E + e], dp = pre[e];
-        dq = fmaf(dp, fabsf(r1), dq);
-        const float d1 = dp * qa[a] * qmix_sgn(r1);
-        raw1[a * L.E + e] = d1;
-        rc[(size_t)(L.r_draw1 + a * L.E + e) * Sn] = d1;
+    sm.RAWF[e * kQmP + lane] = drf;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (a < L.N) {
+        const float r1 = sm.RAW1[(a * L.E + e) * kQmP + lane];
+        dq[a] = fmaf(dp, fabsf(r1), dq[a]);
+        const float d1 = dp * sm.QA[a * kQmP + lane] * qmix_sgn(r1);
+        sm.RAW1[(a * L.E + e) * kQmP + lane] = d1;
+        if (live) rc[(size_t)(L.r_draw1 + a * L.E + e) * Sn] = d1;
       }
-      p.td[((size_t)a * p.B + b) * T + t] = dq;
     }
-    qmix_rows_t(qw + L.wfb, rawf, L.E, L.He, h2, hv);          // hv, pre: scratch from here on
-    for (int j = 0; j < L.He; ++j) rc[(size_t)(L.r_dzf + j) * Sn] = hv[j];
-    qmix_rows_t(qw + L.w1b, raw1, L.N * L.E, L.He, h1, hv);
-    for (int j = 0; j < L.He; ++j) rc[(size_t)(L.r_dz1 + j) * Sn] = hv[j];
   }
-  red[threadIdx.x] = loss; red[kQmixThreads + threadIdx.x] = fill;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) if (a < L.N) sm.RED2[(a * kQmWarps + warp) * kQmP + lane] = dq[a];
   __syncthreads();
-  for (int k = kQmixThreads / 2; k > 0; k >>= 1) {
-    if (threadIdx.x < k) { red[threadIdx.x] += red[threadIdx.x + k]; red[kQmixThreads + threadIdx.x] += red[kQmixThreads + threadIdx.x + k]; }
-    __syncthreads();
+  for (int a = warp; a < L.N; a += kQmWarps) {   // dL/dq_a -> the agents' training pass
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < kQmWarps; ++k) v += sm.RED2[(a * kQmWarps + k) * kQmP + lane];
+    if (live) p.td[((size_t)a * p.B + b) * T + t] = v;
   }
-  if (threadIdx.x == 0) { p.loss_part[4 * blockIdx.x] = red[0]; p.loss_part[4 * blockIdx.x + 1] = red[kQmixThreads]; p.loss_part[4 * blockIdx.x + 2] = 0.f; p.loss_part[4 * blockIdx.x + 3] = 0.f; }
+  qm_layer_t(sm.W + L.wfb, sm.RAWF, sm.H2, L.He, L.E, rc + (size_t)L.r_dzf * Sn, Sn, live, warp, lane);
+  qm_layer_t(sm.W + L.w1b, sm.RAW1, sm.H1, L.He, L.N * L.E, rc + (size_t)L.r_dz1 * Sn, Sn, live, warp, lane);
+  // loss statistics of the tile (warp 0 holds every sample once)
+  if (warp == 0) {
+    float loss = delta * delta * filled, fill = filled;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { loss += __shfl_xor_sync(0xFFFFFFFFu, loss, off); fill += __shfl_xor_sync(0xFFFFFFFFu, fill, off); }
+    if (lane == 0) { p.loss_part[4 * blockIdx.x] = loss; p.loss_part[4 * blockIdx.x + 1] = fill; p.loss_part[4 * blockIdx.x + 2] = 0.f; p.loss_part[4 * blockIdx.x + 3] = 0.f; }
+  }
 }
 
 __global__ void __launch_bounds__(256) qmix_wgrad_kernel(const float* __restrict__ rec, int Sn, const QmixTile* __restrict__ tiles, int chunk_len, float* part, int n) {
@@ -240,6 +311,92 @@ __global__ void __launch_bounds__(256) qmix_wgrad_kernel(const float* __restrict
       if (i < tl.I) dst[tl.woff + o * tl.I + i] = acc[k];
       else if (i == tl.I) dst[tl.boff + o] = acc[k];
     }
+  }
+}
+
+// ---- qmix_wgrad_kernel, second form: the record is read ONCE -----------------------------------------------------------------------------------
+// A CTA owns a run of samples and every (o, i) of every layer: 32 samples of all R record fields at a time in shared memory ([field][33]), each thread
+// accumulates two 4 (outputs) x 8 (inputs) micro-tiles in registers -- 12 shared loads per 32 FMAs, no re-reads of the record from L2 / DRAM (the
+// tile form above reads every field once per tile that needs it: 137 MB instead of 55 MB, and is bound by its 5 shared loads per 4 FMAs).
+// Column I of a layer is its bias: a constant-one field; out-of-range rows / columns read a constant-zero field (no branches in the inner loop).
+struct QmixMicro { int d_row, n_o, x_row, i0, I, woff, boff, o0; };
+constexpr int kQmMicroPerRound = 512;   // 2 per thread
+
+inline int qmix_micro_tiles(const QmixLayout& L, QmixMicro* out, int cap) {
+  struct Lay { int O, I, doff, ioff, woff, boff; };
+  const Lay lays[7] = {
+      {L.He, L.S, L.r_dz1, L.r_x, L.w1a, L.b1a}, {L.N * L.E, L.He, L.r_draw1, L.r_h1, L.w1b, L.b1b}, {L.He, L.S, L.r_dzf, L.r_x, L.wfa, L.bfa},
+      {L.E, L.He, L.r_drawf, L.r_h2, L.wfb, L.bfb}, {L.E, L.S, L.r_dhb, L.r_x, L.wb, L.bb}, {L.E, L.S, L.r_dzv, L.r_x, L.wva, L.bva},
+      {1, L.E, L.r_dv, L.r_hv, L.wvb, L.bvb}};
+  int n = 0;
+  for (const Lay& l : lays)
+    for (int o0 = 0; o0 < l.O; o0 += 4)
+      for (int i0 = 0; i0 <= l.I; i0 += 8) {
+        if (n == cap) return -1;
+        out[n++] = QmixMicro{l.doff + o0, l.O - o0 < 4 ? l.O - o0 : 4, l.ioff + i0, i0, l.I, l.woff, l.boff, o0};
+      }
+  return n;
+}
+
+__global__ void __launch_bounds__(256, 2) qmix_wgrad2_kernel(const float* __restrict__ rec, int Sn, int R, const QmixMicro* __restrict__ micro, int n_micro, int round, int per_cta,
+                                                             float* part, int n) {
+  extern __shared__ __align__(16) float fs[];   // [R + 2][33]: the record fields of 32 samples, then the zero and the one field
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ZERO = R * kQmP, ONE = (R + 1) * kQmP;
+  bool on[2]; int dr[2][4], xr[2][8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int m = round * kQmMicroPerRound + q * 256 + (int)threadIdx.x;
+    on[q] = m < n_micro;
+    QmixMicro mt; mt.d_row = 0; mt.n_o = 0; mt.x_row = 0; mt.i0 = 0; mt.I = -1;
+    if (on[q]) mt = micro[m];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dr[q][k] = k < mt.n_o ? (mt.d_row + k) * kQmP : ZERO;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int i = mt.i0 + k; xr[q][k] = i < mt.I ? (mt.x_row + k) * kQmP : i == mt.I ? ONE : ZERO; }
+  }
+  float acc[2][32];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[q][k] = 0.f;
+  if (threadIdx.x < kQmP) { fs[ZERO + threadIdx.x] = 0.f; fs[ONE + threadIdx.x] = 1.f; }
+  const int s_begin = blockIdx.x * per_cta, s_end = min(Sn, s_begin + per_cta);
+  for (int s0 = s_begin; s0 < s_end; s0 += 32) {
+    __syncthreads();
+    const bool valid = s0 + lane < s_end;
+    for (int f = warp; f < R; f += 8) fs[f * kQmP + lane] = valid ? rec[(size_t)f * Sn + s0 + lane] : 0.f;
+    __syncthreads();
+#pragma unroll 2
+    for (int ss = 0; ss < 32; ++ss) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float d[4], x[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[k] = fs[dr[q][k] + ss];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = fs[xr[q][k] + ss];
+#pragma unroll
+        for (int oo = 0; oo < 4; ++oo)
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) acc[q][oo * 8 + ii] = fmaf(d[oo], x[ii], acc[q][oo * 8 + ii]);
+      }
+    }
+  }
+  float* dst = part + (size_t)blockIdx.x * n;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (!on[q]) continue;
+    const QmixMicro mt = micro[round * kQmMicroPerRound + q * 256 + (int)threadIdx.x];
+#pragma unroll
+    for (int oo = 0; oo < 4; ++oo)
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int o = mt.o0 + oo, i = mt.i0 + ii;
+        if (oo < mt.n_o) {
+          if (i < mt.I) dst[mt.woff + o * mt.I + i] = acc[q][oo * 8 + ii];
+          else if (i == mt.I) dst[mt.boff + o] = acc[q][oo * 8 + ii];
+        }
+      }
   }
 }
 

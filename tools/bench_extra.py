@@ -89,6 +89,6 @@ def ia2c():
 
 if __name__ == "__main__":
     torch.cuda.set_device(0)
-    env_sweep()
-    rollout()
-    ia2c()
+    which = sys.argv[1:] or ["env_sweep", "rollout", "ia2c"]   # e.g. `python tools/bench_extra.py env_sweep` (the ncu capture of lbf_step_kernel)
+    for name in which:
+        {"env_sweep": env_sweep, "rollout": rollout, "ia2c": ia2c}[name]()
