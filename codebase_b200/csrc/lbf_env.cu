@@ -243,8 +243,12 @@ __global__ void lbf_get_state_kernel(LbfCfgDev c, LbfStateDev s, int E, int8_t* 
 __global__ void __launch_bounds__(kThreads) lbf_step_kernel(LbfCfgDev c, LbfStateDev s, StepArgs a, TrajDev traj) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int G = c.G, EPW = 32 / G, EPC = (kThreads / 32) * EPW;
-  int8_t* field_s = reinterpret_cast<int8_t*>(smem_raw);                                   // [EPC][pitch]
-  uint32_t* pl_s = reinterpret_cast<uint32_t*>(field_s + (size_t)EPC * c.pitch);            // [EPC][G]
+  // Shared-memory pitch of an env's grid = pitch + 4 bytes, i.e. an ODD number of words: the lanes of a warp work on different envs at the same cell
+  // offset, and with the global pitch (64 B at 8x8: 16 words) every second env fell on the same bank -- 60 % of this kernel's shared wavefronts were
+  // conflicts (profiles/r2_lbf_step.md).
+  const int sp = c.pitch + 4, spw = sp >> 2, p16 = c.pitch >> 4;
+  int8_t* field_s = reinterpret_cast<int8_t*>(smem_raw);                                   // [EPC][sp]
+  uint32_t* pl_s = reinterpret_cast<uint32_t*>(field_s + (size_t)EPC * sp);                 // [EPC][G]
   uint32_t* foods_s = pl_s + EPC * G;                                                       // [EPC][NF]
   int* meta_s = reinterpret_cast<int*>(foods_s + EPC * c.NF);                               // [EPC][4]: nfood, traj slot (-1 = no write), t_next
   float* obs_s = reinterpret_cast<float*>(meta_s + EPC * 4);                                // [EPC][N][D]
@@ -256,15 +260,20 @@ __global__ void __launch_bounds__(kThreads) lbf_step_kernel(LbfCfgDev c, LbfStat
   const uint32_t gbits = (G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u);
   constexpr uint32_t FULL = 0xFFFFFFFFu;
 
-  {  // stage the CTA's grid tile: contiguous n_here*pitch bytes, 128-bit coalesced
+  {  // stage the CTA's grid tile: contiguous n_here*pitch bytes, 128-bit coalesced loads, word stores into the padded rows
     const uint4* src = reinterpret_cast<const uint4*>(s.field + (size_t)e0 * c.pitch);
-    uint4* dst = reinterpret_cast<uint4*>(field_s);
-    for (int i = threadIdx.x; i < n_here * c.pitch / 16; i += kThreads) dst[i] = src[i];
+    uint32_t* dst = reinterpret_cast<uint32_t*>(field_s);
+    for (int i = threadIdx.x; i < n_here * p16; i += kThreads) {
+      const int l = i / p16, q = i - l * p16;
+      const uint4 v = src[i];
+      uint32_t* d = dst + l * spw + 4 * q;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
   }
   __syncthreads();
 
   const bool env_ok = e < a.E;
-  int8_t* f = field_s + (size_t)le * c.pitch;
+  int8_t* f = field_s + (size_t)le * sp;
   const int step0 = env_ok ? s.step[e] : 0;
   const bool active = env_ok && s.active[e];
   const bool alive = active && sub < c.N;
@@ -461,8 +470,12 @@ __global__ void __launch_bounds__(kThreads) lbf_step_kernel(LbfCfgDev c, LbfStat
   // ---- coalesced write-back: grid tile, observation tile, trajectory observations ---------------------------
   {
     uint4* dst = reinterpret_cast<uint4*>(s.field + (size_t)e0 * c.pitch);
-    const uint4* src = reinterpret_cast<const uint4*>(field_s);
-    for (int i = threadIdx.x; i < n_here * c.pitch / 16; i += kThreads) dst[i] = src[i];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(field_s);
+    for (int i = threadIdx.x; i < n_here * p16; i += kThreads) {
+      const int l = i / p16, q = i - l * p16;
+      const uint32_t* w = src + l * spw + 4 * q;
+      dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
   const int per_env = c.N * c.D;
   if (a.obs_out) {
@@ -567,7 +580,7 @@ int marl_lbf_create(const marl_lbf_cfg* cfg, int32_t n_envs, uint64_t seed, uint
   ALLOC0(h->st.stdr_n, E * 4);
 #undef ALLOC0
   const int EPC = (kThreads / 32) * (32 / d.G);
-  h->step_smem = (size_t)EPC * d.pitch + (size_t)EPC * d.G * 4 + (size_t)EPC * d.NF * 4 + (size_t)EPC * 16 + (size_t)EPC * d.N * d.D * 4;
+  h->step_smem = (size_t)EPC * (d.pitch + 4) + (size_t)EPC * d.G * 4 + (size_t)EPC * d.NF * 4 + (size_t)EPC * 16 + (size_t)EPC * d.N * d.D * 4;
   // the attribute is a per-function, process-wide setting: only ever raise it (a second env with a smaller tile must not lower the limit of the first)
   static size_t step_smem_limit = 48 * 1024;
   if (h->step_smem > step_smem_limit) {

@@ -159,28 +159,22 @@ __device__ __forceinline__ float qm_forward(const QmSmem& sm, const QmixLayout& 
   return y;
 }
 
-// the tile's inputs: state = the agents' observations at step t + dt side by side; q_a = chosen Q (dt = 0) or the double-Q / max target pick (dt = 1)
-__device__ __forceinline__ void qm_load_inputs(const QmSmem& sm, const QmixParams& p, int s0, int Sn, int dt) {
+// the tile's inputs: state = the agents' observations at step t + dt side by side; q_a = chosen Q (dt = 0) or the double-Q / max target pick (dt = 1).
+// lane = sample (b, t, episode slot `ep` of this thread's sample); the rows are shared out over the warps
+__device__ __forceinline__ void qm_load_inputs(const QmSmem& sm, const QmixParams& p, bool live, int b, int t, size_t ep, int dt, int warp, int lane) {
   const QmixLayout& L = p.L;
   const int T = p.traj.T;
-  for (int k = threadIdx.x; k < kQmTS * L.S; k += kQmWarps * 32) {
-    const int sl = k / L.S, i = k - sl * L.S, s = s0 + sl;
-    float v = 0.f;
-    if (s < Sn) {
-      const int b = s / T, t = s - b * T, a = i / p.D, d = i - a * p.D;
-      v = p.traj.obs[(((size_t)p.idx[b] * L.N + a) * (T + 1) + t + dt) * p.D + d];
-    }
-    sm.X[i * kQmP + sl] = v;
+  for (int a = 0; a < L.N; ++a) {
+    const float* ob = p.traj.obs + ((ep * L.N + a) * (T + 1) + t + dt) * p.D;
+    for (int d = warp; d < p.D; d += kQmWarps) sm.X[(a * p.D + d) * kQmP + lane] = live ? ob[d] : 0.f;
   }
-  for (int k = threadIdx.x; k < kQmTS * L.N; k += kQmWarps * 32) {
-    const int a = k / kQmTS, sl = k - a * kQmTS, s = s0 + sl;
+  for (int a = warp; a < L.N; a += kQmWarps) {
     float v = 0.f;
-    if (s < Sn) {
-      const int b = s / T, t = s - b * T;
+    if (live) {
       const size_t row = ((size_t)a * p.B + b) * (T + 1) + t + dt;
       const float* q1 = p.q + row * p.A;
       if (dt == 0) {
-        v = q1[p.traj.act[((size_t)p.idx[b] * L.N + a) * T + t]];
+        v = q1[p.traj.act[(ep * L.N + a) * T + t]];
       } else {
         const float* t1 = p.tq + row * p.A;
         if (p.double_q) {
@@ -193,7 +187,7 @@ __device__ __forceinline__ void qm_load_inputs(const QmSmem& sm, const QmixParam
         }
       }
     }
-    sm.QA[a * kQmP + sl] = v;
+    sm.QA[a * kQmP + lane] = v;
   }
 }
 
@@ -213,13 +207,13 @@ __global__ void __launch_bounds__(kQmWarps * 32, 2) qmix_mix_kernel(QmixParams p
   const int n4 = (L.n + 3) >> 2;
   // ---- target: Q_tot' of the picks at t + 1 on the state at t + 1 ----
   for (int i = threadIdx.x; i < n4; i += kQmWarps * 32) reinterpret_cast<float4*>(sm.W)[i] = reinterpret_cast<const float4*>(img_tgt)[i];
-  qm_load_inputs(sm, p, s0, Sn, 1);
+  qm_load_inputs(sm, p, live, b, t, ep, 1, warp, lane);
   __syncthreads();
   const float ytgt = qm_forward(sm, L, warp, lane);
   __syncthreads();
   // ---- online ----
   for (int i = threadIdx.x; i < n4; i += kQmWarps * 32) reinterpret_cast<float4*>(sm.W)[i] = reinterpret_cast<const float4*>(img)[i];
-  qm_load_inputs(sm, p, s0, Sn, 0);
+  qm_load_inputs(sm, p, live, b, t, ep, 0, warp, lane);
   __syncthreads();
   const float y = qm_forward(sm, L, warp, lane);
   const float filled = live ? (float)p.traj.filled[ep * T + t] : 0.f;
@@ -233,9 +227,6 @@ __global__ void __launch_bounds__(kQmWarps * 32, 2) qmix_mix_kernel(QmixParams p
     if (warp == 0) rc[(size_t)L.r_dv * Sn] = dy;
   }
   // per embedding unit: V's hidden layer, w_final, the ELU; PRE <- dL/d(ELU argument), RAWF <- dL/d(w_final before abs), RAW1 <- dL/d(W1 before abs)
-  float dq[MARL_MAX_AGENTS > 8 ? 8 : MARL_MAX_AGENTS];
-#pragma unroll
-  for (int a = 0; a < 8; ++a) dq[a] = 0.f;
   for (int e = warp; e < L.E; e += kQmWarps) {
     const float pe = sm.PRE[e * kQmP + lane], hid = pe > 0.f ? pe : expm1f(pe), rf = sm.RAWF[e * kQmP + lane], hv = sm.HV[e * kQmP + lane];
     const float dp = dy * fabsf(rf) * (pe > 0.f ? 1.f : hid + 1.f);
@@ -247,19 +238,20 @@ __global__ void __launch_bounds__(kQmWarps * 32, 2) qmix_mix_kernel(QmixParams p
       rc[(size_t)(L.r_dhb + e) * Sn] = dp;
     }
     sm.RAWF[e * kQmP + lane] = drf;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      if (a < L.N) {
-        const float r1 = sm.RAW1[(a * L.E + e) * kQmP + lane];
-        dq[a] = fmaf(dp, fabsf(r1), dq[a]);
-        const float d1 = dp * sm.QA[a * kQmP + lane] * qmix_sgn(r1);
-        sm.RAW1[(a * L.E + e) * kQmP + lane] = d1;
-        if (live) rc[(size_t)(L.r_draw1 + a * L.E + e) * Sn] = d1;
-      }
-    }
+    sm.PRE[e * kQmP + lane] = dp;     // (this thread's own entries: the next loop reads them back without a barrier)
   }
-#pragma unroll
-  for (int a = 0; a < 8; ++a) if (a < L.N) sm.RED2[(a * kQmWarps + warp) * kQmP + lane] = dq[a];
+  for (int a = 0; a < L.N; ++a) {
+    const float qa = sm.QA[a * kQmP + lane];
+    float dq = 0.f;
+    for (int e = warp; e < L.E; e += kQmWarps) {
+      const float dp = sm.PRE[e * kQmP + lane], r1 = sm.RAW1[(a * L.E + e) * kQmP + lane];
+      dq = fmaf(dp, fabsf(r1), dq);
+      const float d1 = dp * qa * qmix_sgn(r1);
+      sm.RAW1[(a * L.E + e) * kQmP + lane] = d1;
+      if (live) rc[(size_t)(L.r_draw1 + a * L.E + e) * Sn] = d1;
+    }
+    sm.RED2[(a * kQmWarps + warp) * kQmP + lane] = dq;
+  }
   __syncthreads();
   for (int a = warp; a < L.N; a += kQmWarps) {   // dL/dq_a -> the agents' training pass
     float v = 0.f;
@@ -404,9 +396,13 @@ __global__ void __launch_bounds__(256, 2) qmix_wgrad2_kernel(const float* __rest
 __global__ void __launch_bounds__(256) qmix_reduce_kernel(const float* __restrict__ part, int chunks, int n, float* grad, const float* __restrict__ loss_part, int n_loss_parts) {
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j < n) {
-    float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += part[(size_t)c * n + j];
-    grad[j] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains (the loads of a chain are dependent on nothing but the index): fixed order
+    int c = 0;
+    for (; c + 3 < chunks; c += 4) {
+      s0 += part[(size_t)c * n + j]; s1 += part[(size_t)(c + 1) * n + j]; s2 += part[(size_t)(c + 2) * n + j]; s3 += part[(size_t)(c + 3) * n + j];
+    }
+    for (; c < chunks; ++c) s0 += part[(size_t)c * n + j];
+    grad[j] = (s0 + s1) + (s2 + s3);
   }
   if (blockIdx.x == 0 && threadIdx.x < 64) {
     const int which = threadIdx.x >> 5, l = threadIdx.x & 31;
