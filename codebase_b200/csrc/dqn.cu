@@ -294,11 +294,20 @@ int marl_dqn_qmix_init(marl_dqn* h, int32_t embed_dim, int32_t hypernet_layers, 
   if (dqn_alloc(reinterpret_cast<float**>(&h->mix_micro), (size_t)nm * sizeof(QmixMicro) / 4)) return MARL_ENOMEM;
   MARL_CUDA_TRY(cudaMemcpy(h->mix_micro, micro.data(), (size_t)nm * sizeof(QmixMicro), cudaMemcpyHostToDevice));
   h->mix_n_micro = nm;
+  static size_t mix_limits[64] = {}, wg_limits[64] = {};   // per device (one process normally drives one GPU)
+  size_t& mix_smem_limit = mix_limits[h->device & 63]; size_t& wg_smem_limit = wg_limits[h->device & 63];
   const size_t wg_smem = (size_t)(h->ql.R + 2) * kQmP * sizeof(float);
   const char* ev = getenv("MARL_QMIX_WGRAD_TILES");
   h->mix_wgrad_tiles = (ev != nullptr && ev[0] == '1') || wg_smem > 110 * 1024;   // the single-read form needs all record fields of 32 samples in shared memory
-  if (!h->mix_wgrad_tiles) MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
-  MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qm_smem_bytes(h->ql)));
+  if (!h->mix_wgrad_tiles && wg_smem > wg_smem_limit) {
+    MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
+    wg_smem_limit = wg_smem;
+  }
+  // the attribute is per function, process-wide: only ever raise it (a second learner with a smaller mixer must not lower the first one's limit)
+  if (qm_smem_bytes(h->ql) > mix_smem_limit) {
+    MARL_CUDA_TRY(cudaFuncSetAttribute(qmix_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qm_smem_bytes(h->ql)));
+    mix_smem_limit = qm_smem_bytes(h->ql);
+  }
   return MARL_OK;
 }
 int marl_dqn_qmix_ptrs(marl_dqn* h, float** mix, float** mix_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params) {

@@ -192,3 +192,18 @@ def test_gpu_update_n_and_state_dict_round_trip():
     m2.load_state_dict(sd)
     assert torch.equal(m2.mix, m.mix) and torch.equal(m2.mix_tgt, m.mix_tgt) and torch.equal(m2.theta, m.theta)
     m.close(); m2.close()
+
+
+@pytest.mark.gpu
+def test_gpu_two_learners_of_different_size_coexist():
+    """The kernels' shared-memory opt-in is a per-function, process-wide attribute: creating a second, smaller learner must not lower the limit the
+    first (4 agents: 2.6x the shared memory) still needs."""
+    hp = lr.DqnHP()
+    big = _gpu_model(hp, max_batch=8, n=4, t=6)
+    small = _gpu_model(hp, max_batch=8, n=2, t=6)
+    rng = np.random.default_rng(2)
+    for m, n in ((small, 2), (big, 4), (small, 2)):
+        ts = _to_store(_batch(rng, 8, n=n, t=6), m.device)
+        met = m.update_from_store(ts, torch.arange(8, dtype=torch.int32, device=m.device)).cpu()
+        assert np.isfinite(float(met[0])) and float(met[4]) > 0
+    big.close(); small.close()
