@@ -45,3 +45,21 @@ def test_shipped_overlays_are_not_degenerate():
             warnings.simplefilter("error")
             check_iteration_budget(int(cfg["env"]["parallel_envs"]), 25, total_steps=int(cfg["algorithm"]["total_steps"]),
                                    eval_interval=int(cfg["algorithm"]["eval_interval"]), eps_decay_over=float(cfg["algorithm"].get("eps_decay_over", 1.0)))
+
+
+def test_eval_entry_point_helpers(tmp_path):
+    """codebase_b200.eval (marlbase/eval.py): argument parsing and the latest-checkpoint rule (largest N over checkpoints/model_sN.pt)."""
+    from codebase_b200 import eval as ev
+
+    d = tmp_path / "checkpoints"
+    d.mkdir()
+    for n in (100, 25600, 9000):
+        (d / f"model_s{n}.pt").write_bytes(b"")
+    (d / "model_sX.pt").write_bytes(b""); (d / "notes.txt").write_text("")
+    assert ev.latest_step(str(d)) == 25600
+    with pytest.raises(FileNotFoundError):
+        ev.latest_step(str(tmp_path))
+    a = ev.parse_args(["path=outputs/x", "load_step=9000", "seed=null", "episodes=64"])
+    assert a == dict(path="outputs/x", load_step=9000, seed=None, episodes=64)
+    with pytest.raises(ValueError):
+        ev.parse_args(["checkpoint=foo"])
