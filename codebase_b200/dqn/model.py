@@ -293,6 +293,8 @@ class QMixNetwork(QNetwork):
     def __init__(self, obs_space, action_space, cfg, layers, parameter_sharing, use_rnn, use_orthogonal_init, mixing, device, max_batch=None, max_episode_length=None):
         if bool(getattr(cfg, "standardise_returns", False)):
             raise NotImplementedError("standardise_returns with QMIX is not implemented (qmix.yaml inherits standardise_returns: False)")
+        if int(dict(mixing)["hypernet_layers"]) != 2:
+            raise NotImplementedError(f"mixing.hypernet_layers={dict(mixing)['hypernet_layers']}: only the shipped two-layer hypernetworks (qmix.yaml) are implemented")
         super().__init__(obs_space, action_space, cfg, layers, parameter_sharing, use_rnn, use_orthogonal_init, device, max_batch, max_episode_length)
         mixing = dict(mixing)
         self.embed_dim, self.hypernet_embed = int(mixing["embed_dim"]), int(mixing["hypernet_embed"])

@@ -63,3 +63,17 @@ def test_eval_entry_point_helpers(tmp_path):
     assert a == dict(path="outputs/x", load_step=9000, seed=None, episodes=64)
     with pytest.raises(ValueError):
         ev.parse_args(["checkpoint=foo"])
+
+
+def test_qmix_host_class_rejects_what_the_kernels_do_not_implement():
+    """Unsupported reference options fail loudly in Python, before any native call (no silent fallback): single-layer hypernetworks,
+    standardise_returns with the mixer."""
+    import types
+
+    from codebase_b200.dqn import model as M
+
+    mixing = dict(embed_dim=64, hypernet_layers=1, hypernet_embed=32)
+    with pytest.raises(NotImplementedError, match="hypernet_layers"):
+        M.QMixNetwork([], [], types.SimpleNamespace(standardise_returns=False), [128, 128], False, False, True, mixing, "cuda")
+    with pytest.raises(NotImplementedError, match="standardise_returns"):
+        M.QMixNetwork([], [], types.SimpleNamespace(standardise_returns=True), [128, 128], False, False, True, dict(mixing, hypernet_layers=2), "cuda")
