@@ -310,6 +310,43 @@ int marl_dqn_qmix_init(marl_dqn* h, int32_t embed_dim, int32_t hypernet_layers, 
   }
   return MARL_OK;
 }
+/* Host-only self-check of the QMIX weight-gradient decompositions (no device needed): counts[0 .. n) = how many micro-tile entries of the single-read
+ * kernel write parameter j, counts[n .. 2n) = the same for the 32 x 32 tile form; both must be 1 everywhere.  Returns n through n_params. */
+int marl_debug_qmix_coverage(int32_t n_agents, int32_t state_dim, int32_t embed_dim, int32_t hypernet_embed, int32_t* counts, int64_t cap, int64_t* n_params) {
+  MARL_REQUIRE(n_agents >= 1 && state_dim >= 1 && embed_dim >= 4 && hypernet_embed >= 4 && n_params != nullptr, "marl_debug_qmix_coverage: bad argument");
+  const QmixLayout L = qmix_layout(n_agents, state_dim, embed_dim, hypernet_embed);
+  *n_params = L.n;
+  if (counts == nullptr) return MARL_OK;
+  MARL_REQUIRE(cap >= 2 * (int64_t)L.n, "marl_debug_qmix_coverage: counts needs 2 x %d entries", L.n);
+  for (int j = 0; j < 2 * L.n; ++j) counts[j] = 0;
+  std::vector<QmixMicro> micro(1 << 16);
+  const int nm = qmix_micro_tiles(L, micro.data(), (int)micro.size());
+  MARL_REQUIRE(nm > 0, "marl_debug_qmix_coverage: too many micro-tiles");
+  for (int m = 0; m < nm; ++m) {
+    const QmixMicro& mt = micro[m];
+    for (int oo = 0; oo < mt.n_o; ++oo)
+      for (int ii = 0; ii < 8; ++ii) {
+        const int o = mt.o0 + oo, i = mt.i0 + ii;
+        if (i < mt.I) counts[mt.woff + o * mt.I + i] += 1;
+        else if (i == mt.I) counts[mt.boff + o] += 1;
+      }
+  }
+  std::vector<QmixTile> tiles(kQmixMaxTiles);
+  const int nt = qmix_tiles(L, tiles.data());
+  MARL_REQUIRE(nt > 0, "marl_debug_qmix_coverage: too many tiles");
+  for (int t = 0; t < nt; ++t) {
+    const QmixTile& tl = tiles[t];
+    for (int oo = 0; oo < 32; ++oo)
+      for (int ii = 0; ii < 32; ++ii) {
+        const int o = tl.o0 + oo, i = tl.i0 + ii;
+        if (o >= tl.O) continue;
+        if (i < tl.I) counts[L.n + tl.woff + o * tl.I + i] += 1;
+        else if (i == tl.I) counts[L.n + tl.boff + o] += 1;
+      }
+  }
+  return MARL_OK;
+}
+
 int marl_dqn_qmix_ptrs(marl_dqn* h, float** mix, float** mix_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params) {
   MARL_REQUIRE(h != nullptr && h->mix != nullptr, "marl_dqn_qmix_ptrs: no mixer (marl_dqn_qmix_init)");
   if (mix) *mix = h->mix; if (mix_tgt) *mix_tgt = h->mix_tgt; if (adam_m) *adam_m = h->mix_m; if (adam_v) *adam_v = h->mix_v;

@@ -197,6 +197,11 @@ int marl_dqn_ret_ms_ptrs(marl_dqn* q, float** ret_ms /* mean[n] | var[n] */, dou
  * caller's job), then marl_dqn_sync_target.  marl_dqn_update* then train agents and mixer with the one Adam step of the reference (the gradient
  * clip covers the agents' networks only, dqn/model.py:169-170); target updates (hard / Polyak) include the mixer (433-443). */
 int marl_dqn_qmix_init(marl_dqn* q, int32_t embed_dim, int32_t hypernet_layers, int32_t hypernet_embed);
+/* Host-only self-check of the two weight-gradient decompositions of the mixer (no device needed; tests/test_qmix.py): counts[0 .. n) and
+ * counts[n .. 2n) = how many (micro-)tile entries write each of the n mixer parameters in the single-read form and in the tile form -- 1 everywhere.
+ * counts == NULL just returns n. */
+int marl_debug_qmix_coverage(int32_t n_agents, int32_t state_dim, int32_t embed_dim, int32_t hypernet_embed, int32_t* counts, int64_t cap,
+                             int64_t* n_params);
 int marl_dqn_qmix_ptrs(marl_dqn* q, float** mix, float** mix_tgt, float** adam_m, float** adam_v, float** grad, int64_t* n_params);
 int marl_dqn_param_ptrs(marl_dqn* q, float** theta, float** theta_tgt, float** adam_m, float** adam_v, float** grad,
                         int64_t* n_params);

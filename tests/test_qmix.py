@@ -96,6 +96,25 @@ def test_oracle_matches_golden_vector():
         assert np.quantile(np.abs(mine.numpy() - g[key]), 0.999) < 1e-5, key
 
 
+@pytest.mark.parametrize("n,s,e,he", [(2, 30, 64, 32), (2, 18, 64, 32), (4, 108, 64, 32), (3, 27, 32, 16), (8, 120, 64, 64), (2, 5, 4, 4), (5, 33, 36, 12)])
+def test_weight_gradient_decompositions_cover_every_parameter_exactly_once(n, s, e, he):
+    """Host-side invariant of csrc/qmix.cuh (runs without a GPU, through the C ABI): the micro-tiles of the single-read weight-gradient kernel and the
+    32 x 32 tiles of the first form each write every mixer parameter exactly once, and the parameter count is the reference's."""
+    import ctypes as C
+
+    from codebase_b200 import _native as nat
+
+    lib = nat.lib()
+    npar = C.c_int64()
+    nat.check(lib.marl_debug_qmix_coverage(C.c_int32(n), C.c_int32(s), C.c_int32(e), C.c_int32(he), None, C.c_int64(0), C.byref(npar)), "marl_debug_qmix_coverage")
+    assert npar.value == qr.mixer_size(n, s, e, he)
+    counts = (C.c_int32 * (2 * npar.value))()
+    nat.check(lib.marl_debug_qmix_coverage(C.c_int32(n), C.c_int32(s), C.c_int32(e), C.c_int32(he), counts, C.c_int64(2 * npar.value), C.byref(npar)), "marl_debug_qmix_coverage")
+    c = np.ctypeslib.as_array(counts)
+    assert (c[: npar.value] == 1).all(), "single-read form"
+    assert (c[npar.value:] == 1).all(), "tile form"
+
+
 # ---- GPU: the CUDA mixer + the tensor-core training pass of the agents' networks, through the C ABI ---------------------------------------------
 def _gpu_model(hp, sharing=False, max_batch=64, n=N, d=D, t=T):
     import types
