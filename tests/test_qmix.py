@@ -36,14 +36,15 @@ def _state_from(model, sharing=False):
 
 
 @pytest.mark.refsrc
-@pytest.mark.parametrize("tu", [2.0, 0.05])
-def test_oracle_matches_live_reference(tu):
+@pytest.mark.parametrize("tu,sharing", [(2.0, False), (0.05, False), (2.0, True)])
+def test_oracle_matches_live_reference(tu, sharing):
     from oracle import ref_shim
 
     ref = ref_shim.load()
     torch.manual_seed(11)
-    model = _ref_model(ref, ref_shim, tu)
-    st = _state_from(model)
+    model = _ref_model(ref, ref_shim, tu, sharing)
+    st = _state_from(model, sharing)
+    kind, n_nets = ("networks", 1) if sharing else ("independent", N)
     assert st.mix.numel() == qr.mixer_size(N, N * D, 64, 32)
     rng = np.random.default_rng(5)
     hp = lr.DqnHP(target_update_interval_or_tau=tu)
@@ -53,7 +54,7 @@ def test_oracle_matches_live_reference(tu):
         got = qr.qmix_update(st, b, hp)
         assert abs(got["loss"] - want) <= 1e-5 * max(1.0, abs(want))
     sd = model.state_dict()
-    for mine, theirs in ((st.theta, lr.flat_from_state_dict(sd, "critic.independent", N)), (st.theta_tgt, lr.flat_from_state_dict(sd, "target.independent", N)),
+    for mine, theirs in ((st.theta, lr.flat_from_state_dict(sd, f"critic.{kind}", n_nets)), (st.theta_tgt, lr.flat_from_state_dict(sd, f"target.{kind}", n_nets)),
                          (st.mix, qr.mixer_flat_from_state_dict(sd, "mixer")), (st.mix_tgt, qr.mixer_flat_from_state_dict(sd, "target_mixer"))):
         assert np.quantile(np.abs(mine.numpy() - theirs.numpy()), 0.999) < 1e-5
 
