@@ -5,7 +5,9 @@ configs/default.yaml:28-35).  Returns a vector env whose transition runs in libm
 79-110): `single_observation_space`, `single_action_space`, `observation_space[0].shape[0] == parallel_envs`,
 `reset() -> (tuple of N arrays [P, obs], info)`, `step(actions) -> (obs, rewards [P, N], done [P], truncated [P],
 info)` with same-step autoreset and `info["final_info"][i]` carrying `episode_returns`, `agent{i}/episode_returns`,
-`episode_length`, `episode_time` (marlbase/utils/wrappers.py:36-41).  The native drivers (dqn/train.py, ac/train.py
+`episode_length`, `episode_time` (marlbase/utils/wrappers.py:36-41).  Not provided: gymnasium's `info["final_observation"]` -- the transition kernel
+resets a finished env in the same launch and only the first observation of the next episode leaves it; the reference's drivers never read that key
+(ac/train.py:90-110 use `final_info` only).  The native drivers (dqn/train.py, ac/train.py
 of this package) skip the numpy surface and drive `env.native` with device tensors.
 """
 from __future__ import annotations
