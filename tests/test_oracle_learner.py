@@ -139,3 +139,26 @@ def test_live_reference_update_on_fresh_seed():
         _close(got["loss"], want)
     d = np.abs(st.theta.numpy() - lr.flat_from_state_dict(model.state_dict(), "critic.independent", N).numpy())
     assert np.quantile(d, 0.999) < 1e-5
+
+
+@pytest.mark.parametrize("alg", ["ia2c", "mappo"])
+def test_cpu_actor_critic_loop_collects_the_reference_batch_layout(alg):
+    """oracle/cpu_loop_ac.py (the CPU arm of tools/learning_curve_ac.py): one iteration fills a Batch as ac/train.py:24-119 does -- obs row 0 from
+    reset, `filled` a prefix of ones per env, the done flag of the last filled step set, nothing written after an env finished -- and the update moves
+    the parameters."""
+    from oracle.cpu_loop_ac import CpuAC
+    from oracle.lbf_ref import LBFConfig
+
+    loop = CpuAC(alg, LBFConfig(time_limit=6), parallel_envs=5, seed=3)
+    t, b, infos = loop.collect()
+    assert 1 <= t <= 6 and len(infos) == 5 and all("episode_returns" in i for i in infos)
+    filled = b["filled"].numpy()
+    for i in range(5):
+        L = int(filled[:, i].sum())
+        assert L >= 1 and (filled[:L, i] == 1).all() and (filled[L:, i] == 0).all()
+        assert b["dones"][L, i] == 1 and (b["dones"][:L, i] == 0).all()
+        assert (b["obss"][L + 1:, i] == 0).all() and (b["rewards"][L:, i] == 0).all() and (b["actions"][L:, i] == 0).all()
+        assert (b["obss"][: L + 1, i] != 0).any()
+    before = loop.st.actor.clone()
+    at, ret = loop.iteration()
+    assert at == 0 and loop.step == loop.P * max(1, int(loop.step / loop.P)) and np.isfinite(ret) and not torch.equal(before, loop.st.actor)
